@@ -1,0 +1,734 @@
+// PDE-residual + masked-observation losses and their analytic VJP w.r.t. the denoised estimate (sm_100a).
+//
+// Replaces, per guided step, the reference's ~40 ATen ops and their autograd mirror:
+//   sample.py:336-353  masked observation losses, loss_fn call, weighted combination
+//   sample.py:106-134  laplacian (reflect pad + 3x3 conv, fp64)
+//   pde_losses.py:71-117  heat_loss2 / llg_loss2
+//   tests/test_llg_pde_loss.py:70-117  m x H_eff residual (exchange + applied field; uniaxial anisotropy added)
+// by two passes over the fields:
+//   pass 1 (guidance_reduce_kernel): three global sums, deterministic two-level reduction, scalars finalised by the
+//           last CTA (no host round trip: the reference syncs 6 times per step for .item() / mask.sum());
+//   pass 2 (guidance_vjp_kernel): seed gradient d loss_comb / d x0-hat written once, in the dtype the denoiser
+//           backward consumes.  The residual r (heat) / the field-gradient G_H (LLG) is staged in shared memory
+//           with a one-pixel ring so the transposed stencil K^T needs no second global pass.
+//
+// Numerics: inputs are the denoiser's fp32 output (exactly representable in the reference's fp64 copy,
+// sample.py:325); all arithmetic and all accumulation here is fp64, the result is rounded once on store --
+// the same place the reference's `.to(fp64)` backward rounds (sample.py:325,332).
+//
+// Memory-bound stencil: no tensor cores.  Work is cut into tiles of TILE_PIX pixels (tile_w in {16,32,64,128}
+// chosen from W so narrow grids such as the reference's 64x16 LLG film keep all lanes busy); a persistent grid
+// (SM count x occupancy) strides over tiles; consecutive lanes touch consecutive columns (coalesced 128 B rows).
+
+#include "common.cuh"
+
+namespace dpde {
+namespace {
+
+struct View {
+    const void* p;
+    int dtype;
+    int64_t sb, sc;
+};
+
+struct Params {
+    int B, C, ch_a, H, W, kind, has_a, has_u;
+    int Hg, yg0, ylo, yhi;  // row slab: global height, global row of local row 0, owned local rows [ylo, yhi)
+    int n_u_units, units_per_sample;
+    int tile_w, tile_h, tw_log2, tiles_x, tiles_y;
+    int64_t tiles_per_plane, n_tiles;
+    View x0, dxdt, obs_a, mask_a, obs_u, mask_u;
+    const double* coef;
+    double inv_dx2, w_a, w_u, w_pde, hw;
+    double gamma, alpha, c_ex, c_an, tau, e[3];
+};
+
+struct TileCoord {
+    int b, unit, y0, x0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int64_t t) {
+    const int64_t pu = t / p.tiles_per_plane;
+    const int r = (int)(t - pu * p.tiles_per_plane);
+    TileCoord c;
+    c.b = (int)(pu / p.units_per_sample);
+    c.unit = (int)(pu - (int64_t)c.b * p.units_per_sample);
+    const int ty = r / p.tiles_x;
+    c.y0 = p.ylo + ty * p.tile_h;
+    c.x0 = (r - ty * p.tiles_x) * p.tile_w;
+    return c;
+}
+
+template <typename T>
+__device__ __forceinline__ double ldg_d(const T* p) {
+    return (double)__ldg(p);
+}
+
+// unscaled 5-point sum with reflect boundaries (sample.py:126-133): u[-1] = u[1], u[H] = u[H-2]
+// `y` indexes the local buffer; `gy` is the same row in the global grid of height Hg (gy == y without slabs).
+template <typename T>
+__device__ __forceinline__ double lap5(const T* __restrict__ u, int y, int x, int gy, int Hg, int W, double& centre) {
+    const int yu = (gy == 0) ? y + 1 : y - 1, yd = (gy == Hg - 1) ? y - 1 : y + 1;
+    const int xl = (x == 0) ? 1 : x - 1, xr = (x == W - 1) ? W - 2 : x + 1;
+    const T* row = u + (int64_t)y * W;
+    centre = ldg_d(row + x);
+    return ((ldg_d(u + (int64_t)yu * W + x) + ldg_d(u + (int64_t)yd * W + x)) + (ldg_d(row + xl) + ldg_d(row + xr))) -
+           4.0 * centre;
+}
+
+// weights of the transposed stencil: neighbour q contributes twice when it sits on the boundary line (row/col 0 or
+// n-1) -- its reflect padding read the target twice.
+__device__ __forceinline__ double adj_w(int q, int n) { return (q == 0 || q == n - 1) ? 2.0 : 1.0; }
+
+__device__ __forceinline__ double masked_diff(const View& obs, const View& mask, int b, int ch, int64_t pix, double x,
+                                              double& m) {
+    m = ld_any(mask.p, mask.dtype, (int64_t)b * mask.sb + (int64_t)ch * mask.sc + pix);
+    const double o = ld_any(obs.p, obs.dtype, (int64_t)b * obs.sb + (int64_t)ch * obs.sc + pix);
+    return m * (x - o);  // (mask * (x - obs)), sample.py:340,342
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// heat residual r = dudt - alpha * lap(u)   (pde_losses.py:91-94)
+template <typename T>
+__device__ __forceinline__ double heat_residual(const Params& p, const T* __restrict__ u, const T* __restrict__ dudt,
+                                                double alpha, int y, int x, double& centre) {
+    const double lap = lap5(u, y, x, y + p.yg0, p.Hg, p.W, centre) * p.inv_dx2;
+    const double dt = dudt ? ldg_d(dudt + (int64_t)y * p.W + x) : 0.0;
+    return dt - alpha * lap;
+}
+
+struct LLGPoint {
+    double m[3], Hf[3], a[3], r[3];
+};
+
+// r = dmdt - tau (-gamma m x H - alpha m x (m x H)),  H = h_ext + c_ex lap(m) + c_an (m.e) e
+// (tests/test_llg_pde_loss.py:70-117, pde_losses.py:246-250)
+template <typename T>
+__device__ __forceinline__ void llg_point(const Params& p, const T* __restrict__ m0, int64_t msc,
+                                          const T* __restrict__ d0, int64_t dsc, const double* hext, int y, int x,
+                                          LLGPoint& o) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double lap = lap5(m0 + k * msc, y, x, y + p.yg0, p.Hg, p.W, o.m[k]) * p.inv_dx2;
+        o.Hf[k] = hext[k] + p.c_ex * lap;
+    }
+    if (p.c_an != 0.0) {
+        const double me = p.c_an * (o.m[0] * p.e[0] + o.m[1] * p.e[1] + o.m[2] * p.e[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.Hf[k] += me * p.e[k];
+    }
+    cross3(o.m, o.Hf, o.a);
+    double ma[3];
+    cross3(o.m, o.a, ma);
+    const int64_t pix = (int64_t)y * p.W + x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double rhs = -p.gamma * o.a[k] - p.alpha * ma[k];
+        const double dt = d0 ? ldg_d(d0 + k * dsc + pix) : 0.0;
+        o.r[k] = dt - rhs * p.tau;
+    }
+}
+
+// sums -> losses and seed coefficients (sample.py:340-353; pde_losses.py:94,116)
+__device__ __forceinline__ void finalize_scalars(const Params& p, const double* sums, double* scal, float* trace) {
+    const double la = p.has_a ? sqrt(sums[0]) : 0.0;
+    const double lu = p.has_u ? sqrt(sums[1]) : 0.0;
+    double lp = 0.0, cp = 0.0;
+    if (p.kind == DPDE_PDE_HEAT) {
+        lp = sqrt(sums[2] / p.hw);
+        cp = p.w_pde / (p.hw * lp);
+    } else if (p.kind == DPDE_PDE_LLG_NORM || p.kind == DPDE_PDE_LLG_RESIDUAL) {
+        const double root = sqrt(sums[2]);
+        lp = root / p.hw;
+        cp = p.w_pde / (root * p.hw);
+    }
+    const double comb = (p.w_a * la + p.w_u * lu) + p.w_pde * lp;
+    scal[0] = la;
+    scal[1] = lu;
+    scal[2] = lp;
+    scal[3] = comb;
+    scal[4] = p.has_a ? p.w_a / la : 0.0;
+    scal[5] = p.has_u ? p.w_u / lu : 0.0;
+    scal[6] = cp;
+    scal[7] = 0.0;
+    if (trace) {
+        trace[0] = (float)la;
+        trace[1] = (float)lu;
+        trace[2] = (float)lp;
+        trace[3] = (float)comb;
+    }
+}
+
+// =========================================================================================================
+// pass 1: global sums
+// =========================================================================================================
+template <typename T, int KIND, int TILE_PIX>
+__global__ void __launch_bounds__(kThreads)
+guidance_reduce_kernel(const __grid_constant__ Params p, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                       double* __restrict__ sums, int finalize, double* __restrict__ scal, float* __restrict__ trace) {
+    constexpr int PPT = TILE_PIX / kThreads;
+    __shared__ double scratch[3 * (kThreads / 32)];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    double s_a = 0.0, s_u = 0.0, s_p = 0.0;
+    const T* x0 = reinterpret_cast<const T*>(p.x0.p);
+    const T* dx = reinterpret_cast<const T*>(p.dxdt.p);
+
+    for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        if (tc.unit < p.ch_a) {  // ---- initial-condition channel: observation loss only
+            if (!p.has_a) continue;
+            const T* a = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)tc.unit * p.x0.sc;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, y = tc.y0 + (e >> p.tw_log2), x = tc.x0 + (e & (p.tile_w - 1));
+                if (y < p.yhi && x < p.W) {
+                    double m;
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    const double d = masked_diff(p.obs_a, p.mask_a, tc.b, tc.unit, pix, ldg_d(a + pix), m);
+                    s_a += d * d;
+                }
+            }
+            continue;
+        }
+        const int cu = tc.unit - p.ch_a;  // u-unit index
+        if (KIND == DPDE_PDE_HEAT || KIND == DPDE_PDE_NONE) {
+            const int ch = p.ch_a + cu;
+            const T* u = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)ch * p.x0.sc;
+            const T* du = dx ? dx + (int64_t)tc.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc : nullptr;
+            const double alpha = (KIND == DPDE_PDE_HEAT) ? __ldg(p.coef + tc.b) : 0.0;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, y = tc.y0 + (e >> p.tw_log2), x = tc.x0 + (e & (p.tile_w - 1));
+                if (y < p.yhi && x < p.W) {
+                    double uc;
+                    if (KIND == DPDE_PDE_HEAT) {
+                        const double r = heat_residual(p, u, du, alpha, y, x, uc);
+                        s_p += r * r;
+                    } else {
+                        uc = ldg_d(u + (int64_t)y * p.W + x);
+                    }
+                    if (p.has_u) {
+                        double m;
+                        const double d = masked_diff(p.obs_u, p.mask_u, tc.b, cu, (int64_t)y * p.W + x, uc, m);
+                        s_u += d * d;
+                    }
+                }
+            }
+        } else {  // LLG kinds: one unit = the 3-component magnetisation
+            const T* m0 = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)p.ch_a * p.x0.sc;
+            const T* d0 = dx ? dx + (int64_t)tc.b * p.dxdt.sb + (int64_t)p.ch_a * p.dxdt.sc : nullptr;
+            double hext[3] = {0.0, 0.0, 0.0};
+            if (KIND == DPDE_PDE_LLG_RESIDUAL) {
+                hext[0] = __ldg(p.coef + 3 * tc.b);
+                hext[1] = __ldg(p.coef + 3 * tc.b + 1);
+                hext[2] = __ldg(p.coef + 3 * tc.b + 2);
+            }
+#pragma unroll 1
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, y = tc.y0 + (e >> p.tw_log2), x = tc.x0 + (e & (p.tile_w - 1));
+                if (y < p.yhi && x < p.W) {
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    double mv[3];
+                    if (KIND == DPDE_PDE_LLG_RESIDUAL) {
+                        LLGPoint q;
+                        llg_point(p, m0, p.x0.sc, d0, p.dxdt.sc, hext, y, x, q);
+                        s_p += (q.r[0] * q.r[0] + q.r[1] * q.r[1]) + q.r[2] * q.r[2];
+                        mv[0] = q.m[0]; mv[1] = q.m[1]; mv[2] = q.m[2];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) mv[c] = ldg_d(m0 + c * p.x0.sc + pix);
+                        const double n = sqrt((mv[0] * mv[0] + mv[1] * mv[1]) + mv[2] * mv[2]);
+                        s_p += (1.0 - n) * (1.0 - n);  // pde_losses.py:115-116
+                    }
+                    if (p.has_u) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            double m;
+                            const double d = masked_diff(p.obs_u, p.mask_u, tc.b, c, pix, mv[c], m);
+                            s_u += d * d;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- CTA partial -> global, last CTA combines all partials in a fixed order (deterministic)
+    block_sum3(s_a, s_u, s_p, scratch);
+    if (tid == 0) {
+        partials[3 * blockIdx.x + 0] = s_a;
+        partials[3 * blockIdx.x + 1] = s_u;
+        partials[3 * blockIdx.x + 2] = s_p;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
+        a += __ldcg(partials + 3 * i);
+        b += __ldcg(partials + 3 * i + 1);
+        c += __ldcg(partials + 3 * i + 2);
+    }
+    block_sum3(a, b, c, scratch);
+    if (tid == 0) {
+        sums[0] = a;
+        sums[1] = b;
+        sums[2] = c;
+        if (finalize) finalize_scalars(p, sums, scal, trace);
+        *ticket = 0u;
+    }
+}
+
+__global__ void finalize_kernel(const __grid_constant__ Params p, const double* __restrict__ sums,
+                                double* __restrict__ scal, float* __restrict__ trace) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) finalize_scalars(p, sums, scal, trace);
+}
+
+// =========================================================================================================
+// pass 2: seed gradient
+// =========================================================================================================
+// ring position e in [0, 2*(tw+2) + 2*th) -> tile-relative (ry, rx) in [-1, th] x [-1, tw]
+__device__ __forceinline__ void ring_coord(int e, int th, int tw, int& ry, int& rx) {
+    const int SW = tw + 2;
+    if (e < SW) {
+        ry = -1;
+        rx = e - 1;
+    } else if (e < 2 * SW) {
+        ry = th;
+        rx = e - SW - 1;
+    } else {
+        const int j = e - 2 * SW;
+        ry = j >> 1;
+        rx = (j & 1) ? tw : -1;
+    }
+}
+
+template <typename T, int KIND, int TILE_PIX>
+__global__ void __launch_bounds__(kThreads)
+guidance_vjp_kernel(const __grid_constant__ Params p, const double* __restrict__ scal, const double* __restrict__ upstream,
+                    T* __restrict__ g_x0, T* __restrict__ g_dxdt) {
+    constexpr int PPT = TILE_PIX / kThreads;
+    constexpr bool STENCIL = (KIND == DPDE_PDE_HEAT || KIND == DPDE_PDE_LLG_RESIDUAL);
+    // widest staged tile: (TILE_PIX/128 + 2) x (128 + 2) pixels, 1 (heat) or 3 (LLG) doubles each
+    constexpr int STAGE = (TILE_PIX / 128 + 2) * 130;
+    constexpr int NCOMP = (KIND == DPDE_PDE_LLG_RESIDUAL) ? 3 : 1;
+    __shared__ double stage[STENCIL ? NCOMP * STAGE : 1];
+
+    const int tid = threadIdx.x;
+    const double up = upstream ? __ldg(upstream) : 1.0;
+    const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
+    const T* x0 = reinterpret_cast<const T*>(p.x0.p);
+    const T* dx = reinterpret_cast<const T*>(p.dxdt.p);
+    const int64_t plane = (int64_t)p.H * p.W;
+    const int SW = p.tile_w + 2;
+
+    for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        if (tc.unit < p.ch_a) {  // ---- a-channel: g = c_a * mask * (mask * (a - obs))
+            const T* a = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)tc.unit * p.x0.sc;
+            T* g = g_x0 + ((int64_t)tc.b * p.C + tc.unit) * plane;
+            T* gd = g_dxdt ? g_dxdt + ((int64_t)tc.b * p.C + tc.unit) * plane : nullptr;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, y = tc.y0 + (e >> p.tw_log2), x = tc.x0 + (e & (p.tile_w - 1));
+                if (y < p.yhi && x < p.W) {
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    double v = 0.0;
+                    if (p.has_a) {
+                        double m;
+                        const double d = masked_diff(p.obs_a, p.mask_a, tc.b, tc.unit, pix, ldg_d(a + pix), m);
+                        v = c_a * (m * d);
+                    }
+                    g[pix] = (T)v;
+                    if (gd) gd[pix] = (T)0;
+                }
+            }
+            continue;
+        }
+        const int cu = tc.unit - p.ch_a;
+
+        if (KIND == DPDE_PDE_HEAT || KIND == DPDE_PDE_NONE) {
+            const int ch = p.ch_a + cu;
+            const T* u = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)ch * p.x0.sc;
+            const T* du = dx ? dx + (int64_t)tc.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc : nullptr;
+            T* g = g_x0 + ((int64_t)tc.b * p.C + ch) * plane;
+            T* gd = g_dxdt ? g_dxdt + ((int64_t)tc.b * p.C + ch) * plane : nullptr;
+            const double alpha = (KIND == DPDE_PDE_HEAT) ? __ldg(p.coef + tc.b) : 0.0;
+            double uc[PPT];
+            if (KIND == DPDE_PDE_HEAT) {
+                // phase 1: residual on the tile's own pixels; phase 2: on its one-pixel ring
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    const int e = k * kThreads + tid, ly = e >> p.tw_log2, lx = e & (p.tile_w - 1);
+                    const int y = tc.y0 + ly, x = tc.x0 + lx;
+                    double r = 0.0;
+                    uc[k] = 0.0;
+                    if (y < p.yhi && x < p.W) r = heat_residual(p, u, du, alpha, y, x, uc[k]);
+                    stage[(ly + 1) * SW + lx + 1] = r;
+                }
+                const int ring = 2 * SW + 2 * p.tile_h;
+                for (int e = tid; e < ring; e += kThreads) {
+                    int ry, rx;
+                    ring_coord(e, p.tile_h, p.tile_w, ry, rx);
+                    const int y = tc.y0 + ry, x = tc.x0 + rx;
+                    double r = 0.0, dummy;
+                    if (y >= 0 && y < p.H && y + p.yg0 >= 0 && y + p.yg0 < p.Hg && x >= 0 && x < p.W) r = heat_residual(p, u, du, alpha, y, x, dummy);
+                    stage[(ry + 1) * SW + rx + 1] = r;
+                }
+                __syncthreads();
+            }
+            // phase 3: g_u = c_u mask (mask (u - obs)) - c_p (alpha/dx^2) K^T r ;  g_dudt = c_p r
+            const double kp = -c_p * alpha * p.inv_dx2;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, ly = e >> p.tw_log2, lx = e & (p.tile_w - 1);
+                const int y = tc.y0 + ly, x = tc.x0 + lx;
+                if (y < p.yhi && x < p.W) {
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    double v = 0.0;
+                    if (KIND == DPDE_PDE_HEAT) {
+                        const double* c = &stage[(ly + 1) * SW + lx + 1];
+                        const double acc = ((adj_w(y + p.yg0 - 1, p.Hg) * c[-SW] + adj_w(y + p.yg0 + 1, p.Hg) * c[SW]) +
+                                            (adj_w(x - 1, p.W) * c[-1] + adj_w(x + 1, p.W) * c[1])) - 4.0 * c[0];
+                        v = kp * acc;
+                        if (gd) gd[pix] = (T)(c_p * c[0]);
+                    } else {
+                        uc[k] = ldg_d(u + pix);
+                        if (gd) gd[pix] = (T)0;
+                    }
+                    if (p.has_u) {
+                        double m;
+                        const double d = masked_diff(p.obs_u, p.mask_u, tc.b, cu, pix, uc[k], m);
+                        v += c_u * (m * d);
+                    }
+                    g[pix] = (T)v;
+                }
+            }
+            if (KIND == DPDE_PDE_HEAT) __syncthreads();  // stage is reused by the next tile
+        } else if (KIND == DPDE_PDE_LLG_NORM) {
+            // g_m = -c_p (1 - n) m / n  (0 where n == 0, as torch.linalg.norm's backward)  + observation term
+            const T* m0 = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)p.ch_a * p.x0.sc;
+            T* g = g_x0 + ((int64_t)tc.b * p.C + p.ch_a) * plane;
+            T* gd = g_dxdt ? g_dxdt + ((int64_t)tc.b * p.C + p.ch_a) * plane : nullptr;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, y = tc.y0 + (e >> p.tw_log2), x = tc.x0 + (e & (p.tile_w - 1));
+                if (y < p.yhi && x < p.W) {
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    double mv[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) mv[c] = ldg_d(m0 + c * p.x0.sc + pix);
+                    const double n = sqrt((mv[0] * mv[0] + mv[1] * mv[1]) + mv[2] * mv[2]);
+                    const double f = (n > 0.0) ? -c_p * (1.0 - n) / n : 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double v = f * mv[c];
+                        if (p.has_u) {
+                            double m;
+                            const double d = masked_diff(p.obs_u, p.mask_u, tc.b, c, pix, mv[c], m);
+                            v += c_u * (m * d);
+                        }
+                        g[c * plane + pix] = (T)v;
+                        if (gd) gd[c * plane + pix] = (T)0;
+                    }
+                }
+            }
+        } else {  // ---- LLG m x H_eff residual
+            const T* m0 = x0 + (int64_t)tc.b * p.x0.sb + (int64_t)p.ch_a * p.x0.sc;
+            const T* d0 = dx ? dx + (int64_t)tc.b * p.dxdt.sb + (int64_t)p.ch_a * p.dxdt.sc : nullptr;
+            T* g = g_x0 + ((int64_t)tc.b * p.C + p.ch_a) * plane;
+            T* gd = g_dxdt ? g_dxdt + ((int64_t)tc.b * p.C + p.ch_a) * plane : nullptr;
+            const double hext[3] = {__ldg(p.coef + 3 * tc.b), __ldg(p.coef + 3 * tc.b + 1), __ldg(p.coef + 3 * tc.b + 2)};
+            double local[PPT][3];  // -tau [G_m + c_an (e.G_H) e] + observation term, per own pixel
+            // With seed s = c_p r, q = s x m:  G_H = -gamma q - alpha (q x m),
+            //                                   G_m = -gamma (H x s) - alpha (a x s + H x q)
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, ly = e >> p.tw_log2, lx = e & (p.tile_w - 1);
+                const int y = tc.y0 + ly, x = tc.x0 + lx;
+                double GH[3] = {0.0, 0.0, 0.0};
+                local[k][0] = local[k][1] = local[k][2] = 0.0;
+                if (y < p.yhi && x < p.W) {
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    LLGPoint q;
+                    llg_point(p, m0, p.x0.sc, d0, p.dxdt.sc, hext, y, x, q);
+                    double s[3] = {c_p * q.r[0], c_p * q.r[1], c_p * q.r[2]}, qq[3], qm[3], Hs[3], as[3], Hq[3];
+                    cross3(s, q.m, qq);
+                    cross3(qq, q.m, qm);
+                    cross3(q.Hf, s, Hs);
+                    cross3(q.a, s, as);
+                    cross3(q.Hf, qq, Hq);
+                    double eG = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        GH[c] = -p.gamma * qq[c] - p.alpha * qm[c];
+                        eG += p.e[c] * GH[c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const double Gm = -p.gamma * Hs[c] - p.alpha * (as[c] + Hq[c]);
+                        double v = -p.tau * (Gm + p.c_an * eG * p.e[c]);
+                        if (p.has_u) {
+                            double m;
+                            const double d = masked_diff(p.obs_u, p.mask_u, tc.b, c, pix, q.m[c], m);
+                            v += c_u * (m * d);
+                        }
+                        local[k][c] = v;
+                        if (gd) gd[c * plane + pix] = (T)s[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) stage[c * STAGE + (ly + 1) * SW + lx + 1] = GH[c];
+            }
+            const int ring = 2 * SW + 2 * p.tile_h;
+            for (int e = tid; e < ring; e += kThreads) {
+                int ry, rx;
+                ring_coord(e, p.tile_h, p.tile_w, ry, rx);
+                const int y = tc.y0 + ry, x = tc.x0 + rx;
+                double GH[3] = {0.0, 0.0, 0.0};
+                if (y >= 0 && y < p.H && y + p.yg0 >= 0 && y + p.yg0 < p.Hg && x >= 0 && x < p.W) {
+                    LLGPoint q;
+                    llg_point(p, m0, p.x0.sc, d0, p.dxdt.sc, hext, y, x, q);
+                    double s[3] = {c_p * q.r[0], c_p * q.r[1], c_p * q.r[2]}, qq[3], qm[3];
+                    cross3(s, q.m, qq);
+                    cross3(qq, q.m, qm);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) GH[c] = -p.gamma * qq[c] - p.alpha * qm[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) stage[c * STAGE + (ry + 1) * SW + rx + 1] = GH[c];
+            }
+            __syncthreads();
+            const double kx = -p.tau * p.c_ex * p.inv_dx2;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int e = k * kThreads + tid, ly = e >> p.tw_log2, lx = e & (p.tile_w - 1);
+                const int y = tc.y0 + ly, x = tc.x0 + lx;
+                if (y < p.yhi && x < p.W) {
+                    const int64_t pix = (int64_t)y * p.W + x;
+                    const double wu = adj_w(y + p.yg0 - 1, p.Hg), wd = adj_w(y + p.yg0 + 1, p.Hg), wl = adj_w(x - 1, p.W), wr = adj_w(x + 1, p.W);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const double* s = &stage[c * STAGE + (ly + 1) * SW + lx + 1];
+                        const double acc = ((wu * s[-SW] + wd * s[SW]) + (wl * s[-1] + wr * s[1])) - 4.0 * s[0];
+                        g[c * plane + pix] = (T)(local[k][c] + kx * acc);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// =========================================================================================================
+// stand-alone laplacian(u, dx) and its transpose (Level-1 op, sample.py:106-134)
+// =========================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+laplacian_kernel(const T* __restrict__ u, T* __restrict__ out, int64_t planes, int H, int W, int64_t stride_in,
+                 double inv_dx2, int adjoint) {
+    const int64_t hw = (int64_t)H * W, total = planes * hw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pl = i / hw;
+        const int r = (int)(i - pl * hw), y = r / W, x = r - y * W;
+        const T* src = u + pl * stride_in;
+        double v;
+        if (!adjoint) {
+            double c;
+            v = lap5(src, y, x, y, H, W, c);
+        } else {
+            const T* row = src + (int64_t)y * W;
+            v = -4.0 * ldg_d(row + x);
+            if (y > 0) v += adj_w(y - 1, H) * ldg_d(row - W + x);
+            if (y < H - 1) v += adj_w(y + 1, H) * ldg_d(row + W + x);
+            if (x > 0) v += adj_w(x - 1, W) * ldg_d(row + x - 1);
+            if (x < W - 1) v += adj_w(x + 1, W) * ldg_d(row + x + 1);
+        }
+        out[i] = (T)(v * inv_dx2);
+    }
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }
+
+int validate_and_fill(const dpde_guidance_desc* d, int tile_pix, Params& p, const char* who) {
+    if (!d) return fail(DPDE_ERR_INVALID, "%s: desc is NULL", who);
+    if (d->B < 1 || d->C < 1 || d->ch_a < 0 || d->ch_a > d->C) return fail(DPDE_ERR_INVALID, "%s: bad B/C/ch_a", who);
+    if (d->H < 2 || d->W < 2) return fail(DPDE_ERR_INVALID, "%s: H and W must be >= 2 (reflect padding)", who);
+    if (!d->x0.ptr) return fail(DPDE_ERR_INVALID, "%s: x0 is NULL", who);
+    if (d->x0.dtype != DPDE_F32 && d->x0.dtype != DPDE_F64) return fail(DPDE_ERR_UNSUPPORTED, "%s: x0 must be f32/f64", who);
+    if (d->dxdt.ptr && d->dxdt.dtype != d->x0.dtype) return fail(DPDE_ERR_INVALID, "%s: dxdt dtype != x0 dtype", who);
+    const int cu = d->C - d->ch_a;
+    switch (d->pde_kind) {
+        case DPDE_PDE_NONE: break;
+        case DPDE_PDE_HEAT:
+            if (cu < 1) return fail(DPDE_ERR_INVALID, "%s: heat residual needs at least one u channel", who);
+            if (!d->sample_coef) return fail(DPDE_ERR_INVALID, "%s: heat residual needs sample_coef = alpha (B,)", who);
+            break;
+        case DPDE_PDE_LLG_RESIDUAL:
+            if (!d->sample_coef) return fail(DPDE_ERR_INVALID, "%s: LLG residual needs sample_coef = h_ext (B,3)", who);
+            /* fallthrough */
+        case DPDE_PDE_LLG_NORM:
+            if (cu != 3) return fail(DPDE_ERR_INVALID, "%s: LLG kinds need exactly 3 magnetisation channels, got %d", who, cu);
+            break;
+        default: return fail(DPDE_ERR_INVALID, "%s: unknown pde_kind %d", who, d->pde_kind);
+    }
+    if (d->pde_kind != DPDE_PDE_NONE && d->pde_kind != DPDE_PDE_LLG_NORM && !(d->dx > 0.0))
+        return fail(DPDE_ERR_INVALID, "%s: dx must be > 0", who);
+    if (d->has_a && (d->ch_a < 1 || !d->obs_a.ptr || !d->mask_a.ptr)) return fail(DPDE_ERR_INVALID, "%s: has_a without obs_a/mask_a", who);
+    if (d->has_u && (cu < 1 || !d->obs_u.ptr || !d->mask_u.ptr)) return fail(DPDE_ERR_INVALID, "%s: has_u without obs_u/mask_u", who);
+
+    p.B = d->B; p.C = d->C; p.ch_a = d->ch_a; p.H = d->H; p.W = d->W; p.kind = d->pde_kind;
+    if (d->slab_H_global > 0) {
+        const int need = (d->pde_kind == DPDE_PDE_HEAT || d->pde_kind == DPDE_PDE_LLG_RESIDUAL) ? 2 : 0;
+        if (d->slab_halo < need) return fail(DPDE_ERR_INVALID, "%s: slab_halo %d < %d needed by this residual", who, d->slab_halo, need);
+        if (d->H - 2 * d->slab_halo < 1 || d->slab_row0 < 0 || d->slab_row0 + (d->H - 2 * d->slab_halo) > d->slab_H_global)
+            return fail(DPDE_ERR_INVALID, "%s: slab rows [%d, %d) outside the global grid of %d rows", who, d->slab_row0,
+                        d->slab_row0 + d->H - 2 * d->slab_halo, d->slab_H_global);
+        p.Hg = d->slab_H_global; p.ylo = d->slab_halo; p.yhi = d->H - d->slab_halo; p.yg0 = d->slab_row0 - d->slab_halo;
+    } else {
+        p.Hg = d->H; p.ylo = 0; p.yhi = d->H; p.yg0 = 0;
+    }
+    p.has_a = d->has_a != 0; p.has_u = d->has_u != 0;
+    const bool llg = d->pde_kind == DPDE_PDE_LLG_NORM || d->pde_kind == DPDE_PDE_LLG_RESIDUAL;
+    p.n_u_units = llg ? 1 : cu;
+    p.units_per_sample = d->ch_a + p.n_u_units;
+    p.tile_w = d->W > 64 ? 128 : d->W > 32 ? 64 : d->W > 16 ? 32 : 16;
+    p.tile_h = tile_pix / p.tile_w;
+    p.tw_log2 = p.tile_w == 128 ? 7 : p.tile_w == 64 ? 6 : p.tile_w == 32 ? 5 : 4;
+    p.tiles_x = (d->W + p.tile_w - 1) / p.tile_w;
+    p.tiles_y = (p.yhi - p.ylo + p.tile_h - 1) / p.tile_h;
+    p.tiles_per_plane = (int64_t)p.tiles_x * p.tiles_y;
+    p.n_tiles = p.tiles_per_plane * p.units_per_sample * d->B;
+    p.x0 = to_view(d->x0); p.dxdt = to_view(d->dxdt);
+    p.obs_a = to_view(d->obs_a); p.mask_a = to_view(d->mask_a);
+    p.obs_u = to_view(d->obs_u); p.mask_u = to_view(d->mask_u);
+    p.coef = d->sample_coef;
+    p.inv_dx2 = d->dx > 0.0 ? 1.0 / (d->dx * d->dx) : 0.0;
+    p.w_a = d->w_a; p.w_u = d->w_u; p.w_pde = d->w_pde;
+    p.hw = (double)p.Hg * (double)d->W;
+    p.gamma = d->gamma; p.alpha = d->alpha; p.c_ex = d->c_ex; p.c_an = d->c_an; p.tau = d->tau;
+    p.e[0] = d->easy_axis[0]; p.e[1] = d->easy_axis[1]; p.e[2] = d->easy_axis[2];
+    return DPDE_OK;
+}
+
+template <typename K>
+int persistent_grid(K kernel, int64_t n_tiles) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    int64_t g = (int64_t)sm_count() * occ;
+    if (g > n_tiles) g = n_tiles;
+    if (g > kMaxPartials) g = kMaxPartials;
+    return (int)(g < 1 ? 1 : g);
+}
+
+constexpr int kTileHeat = 2048, kTileLLG = 1024;
+inline int tile_pix_for(int kind) { return kind == DPDE_PDE_LLG_RESIDUAL ? kTileLLG : kTileHeat; }
+
+template <typename T>
+int launch_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal,
+                  float* trace, cudaStream_t s) {
+#define DPDE_RED(KIND, TP)                                                                              \
+    {                                                                                                   \
+        auto k = guidance_reduce_kernel<T, KIND, TP>;                                                   \
+        k<<<persistent_grid(k, p.n_tiles), kThreads, 0, s>>>(p, partials, ticket, sums, finalize, scal, trace); \
+    }
+    switch (p.kind) {
+        case DPDE_PDE_NONE: DPDE_RED(DPDE_PDE_NONE, kTileHeat) break;
+        case DPDE_PDE_HEAT: DPDE_RED(DPDE_PDE_HEAT, kTileHeat) break;
+        case DPDE_PDE_LLG_NORM: DPDE_RED(DPDE_PDE_LLG_NORM, kTileHeat) break;
+        default: DPDE_RED(DPDE_PDE_LLG_RESIDUAL, kTileLLG) break;
+    }
+#undef DPDE_RED
+    return check_launch("dpde_guidance_reduce");
+}
+
+template <typename T>
+int launch_vjp(const Params& p, const double* scal, const double* upstream, void* g, void* gd, cudaStream_t s) {
+#define DPDE_VJP(KIND, TP)                                                                   \
+    {                                                                                        \
+        auto k = guidance_vjp_kernel<T, KIND, TP>;                                           \
+        k<<<persistent_grid(k, p.n_tiles), kThreads, 0, s>>>(p, scal, upstream, (T*)g, (T*)gd); \
+    }
+    switch (p.kind) {
+        case DPDE_PDE_NONE: DPDE_VJP(DPDE_PDE_NONE, kTileHeat) break;
+        case DPDE_PDE_HEAT: DPDE_VJP(DPDE_PDE_HEAT, kTileHeat) break;
+        case DPDE_PDE_LLG_NORM: DPDE_VJP(DPDE_PDE_LLG_NORM, kTileHeat) break;
+        default: DPDE_VJP(DPDE_PDE_LLG_RESIDUAL, kTileLLG) break;
+    }
+#undef DPDE_VJP
+    return check_launch("dpde_guidance_vjp");
+}
+
+}  // namespace
+}  // namespace dpde
+
+using namespace dpde;
+
+extern "C" {
+
+size_t dpde_guidance_workspace_bytes(void) { return (size_t)(3 * kMaxPartials + 2) * sizeof(double); }
+
+int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize, double* scalars,
+                         float* trace_row, dpde_stream_t stream) {
+    Params p;
+    if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, "dpde_guidance_reduce")) return rc;
+    if (!workspace || !sums) return fail(DPDE_ERR_INVALID, "dpde_guidance_reduce: workspace/sums is NULL");
+    if (finalize && !scalars) return fail(DPDE_ERR_INVALID, "dpde_guidance_reduce: finalize needs scalars");
+    double* partials = reinterpret_cast<double*>(workspace);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + 3 * kMaxPartials);
+    cudaStream_t s = (cudaStream_t)stream;
+    return p.x0.dtype == DPDE_F32 ? launch_reduce<float>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
+                                  : launch_reduce<double>(p, partials, ticket, sums, finalize, scalars, trace_row, s);
+}
+
+int dpde_guidance_finalize(const dpde_guidance_desc* desc, const double* sums, double* scalars, float* trace_row,
+                           dpde_stream_t stream) {
+    Params p;
+    if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, "dpde_guidance_finalize")) return rc;
+    if (!sums || !scalars) return fail(DPDE_ERR_INVALID, "dpde_guidance_finalize: sums/scalars is NULL");
+    finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, sums, scalars, trace_row);
+    return check_launch("dpde_guidance_finalize");
+}
+
+int dpde_guidance_vjp(const dpde_guidance_desc* desc, const double* scalars, const double* upstream, void* g_x0,
+                      void* g_dxdt, dpde_stream_t stream) {
+    Params p;
+    if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, "dpde_guidance_vjp")) return rc;
+    if (!scalars || !g_x0) return fail(DPDE_ERR_INVALID, "dpde_guidance_vjp: scalars/g_x0 is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    return p.x0.dtype == DPDE_F32 ? launch_vjp<float>(p, scalars, upstream, g_x0, g_dxdt, s)
+                                  : launch_vjp<double>(p, scalars, upstream, g_x0, g_dxdt, s);
+}
+
+int dpde_laplacian(const void* u, void* out, int32_t dtype, int64_t planes, int32_t H, int32_t W, int64_t plane_stride_in,
+                   double dx, int32_t adjoint, dpde_stream_t stream) {
+    if (!u || !out) return fail(DPDE_ERR_INVALID, "dpde_laplacian: null pointer");
+    if (planes < 0 || H < 2 || W < 2) return fail(DPDE_ERR_INVALID, "dpde_laplacian: need planes >= 0, H, W >= 2");
+    if (!(dx > 0.0)) return fail(DPDE_ERR_INVALID, "dpde_laplacian: dx must be > 0");
+    if (dtype != DPDE_F32 && dtype != DPDE_F64) return fail(DPDE_ERR_UNSUPPORTED, "dpde_laplacian: dtype must be f32/f64");
+    if (planes == 0) return DPDE_OK;
+    const int64_t total = planes * (int64_t)H * W;
+    int64_t blocks = (total + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const double inv = 1.0 / (dx * dx);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == DPDE_F32)
+        laplacian_kernel<float><<<(int)blocks, kThreads, 0, s>>>((const float*)u, (float*)out, planes, H, W, plane_stride_in, inv, adjoint);
+    else
+        laplacian_kernel<double><<<(int)blocks, kThreads, 0, s>>>((const double*)u, (double*)out, planes, H, W, plane_stride_in, inv, adjoint);
+    return check_launch("dpde_laplacian");
+}
+
+}  // extern "C"

@@ -12,7 +12,7 @@ north_star keeps the U-Net forward/backward in PyTorch; the sampler accepts any 
   (config 5, 4096^2: GroupNorm is a global spatial statistic and does not slab-decompose).
 
 Nothing here launches our CUDA kernels; it exists so benchmarks and parity tests have a
-denoiser on the GPU box, where ``/root/reference`` is absent.
+denoiser on the GPU box, where the reference source is absent.
 """
 from __future__ import annotations
 

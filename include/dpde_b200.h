@@ -1,0 +1,143 @@
+/*
+ * dpde_b200 -- C ABI of the B200-native physics-guided sampler step.
+ *
+ * Drop-in boundary for ONE hot path of cmt-dtu-energy/dynamical-pde-diffusion: the guided EDM Heun step of
+ * JointSampler.sample (src/diffusion_pde/sampling/sample.py:320-357).  The reference is pure PyTorch and has no
+ * FFI of its own; each entry point below states the reference lines whose math it replaces.  A binding is a
+ * ctypes / cffi stub; dynamical_pde_diffusion_b200/_ffi.py is the one we ship.
+ *
+ * Conventions
+ *   - The caller owns every buffer; all pointers are DEVICE pointers unless stated otherwise.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); nothing synchronises the host.
+ *   - Return value: 0 on success, negative DPDE_ERR_* otherwise; dpde_last_error() gives the message of the
+ *     calling thread's last failure.  No exceptions cross the boundary.
+ *   - Fields are NCHW with contiguous rows (stride_w == 1, stride_h == W); batch and channel strides are free
+ *     (in elements) so channel-slice views such as x_N[:, ch_a:] (sample.py:345-346) pass without a copy, and a
+ *     stride of 0 broadcasts (masks (H,W), observations (1,ch,H,W): sample.py:340-342, model_testing.py:174-193).
+ *   - Reductions are deterministic: per-CTA partial sums are combined in a fixed order.
+ */
+#ifndef DPDE_B200_H
+#define DPDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPDE_ABI_VERSION 1
+
+enum dpde_error { DPDE_OK = 0, DPDE_ERR_INVALID = -1, DPDE_ERR_CUDA = -2, DPDE_ERR_UNSUPPORTED = -3 };
+enum dpde_dtype { DPDE_F32 = 0, DPDE_F64 = 1, DPDE_U8 = 2 };
+
+/* PDE residual plugged into the sampler (the reference's loss_fn slot, sample.py:347). */
+enum dpde_pde_kind {
+    DPDE_PDE_NONE = 0,
+    DPDE_PDE_HEAT = 1,         /* heat_loss2,  pde_losses.py:71-96  + laplacian, sample.py:106-134       */
+    DPDE_PDE_LLG_NORM = 2,     /* llg_loss2,   pde_losses.py:99-117 (soft |m| = 1)                        */
+    DPDE_PDE_LLG_RESIDUAL = 3  /* m x H_eff residual, tests/test_llg_pde_loss.py:70-117 (no demag)        */
+};
+
+typedef void* dpde_stream_t; /* cudaStream_t */
+
+/* A (B, ch, H, W) operand; rows contiguous.  ptr == NULL means "absent" (zeros for dxdt, unused for obs/mask). */
+typedef struct dpde_view {
+    const void* ptr;
+    int32_t dtype;    /* dpde_dtype */
+    int32_t _pad;
+    int64_t stride_b; /* elements between samples;  0 broadcasts over the batch   */
+    int64_t stride_c; /* elements between channels; 0 broadcasts over channels    */
+} dpde_view;
+
+/* One guidance evaluation: everything sample.py:336-353 reads. */
+typedef struct dpde_guidance_desc {
+    int32_t B, C, ch_a, H, W;
+    int32_t pde_kind;          /* dpde_pde_kind; acts on channels [ch_a, C)                               */
+    int32_t has_a, has_u;      /* mask_a.sum() > 0 / mask_u.sum() > 0 (sample.py:339,341), decided once   */
+    /* Row-slab domain decomposition (large grids; not in the reference).  slab_H_global == 0: the fields hold the
+       whole grid.  Otherwise every field is a local buffer of H rows = slab_halo ghost rows + owned rows +
+       slab_halo ghost rows, the first owned row is global row slab_row0 of a grid slab_H_global rows high; sums
+       and gradients cover owned rows only (ghost rows are read, never written).  The heat VJP needs
+       slab_halo >= 2, LLG_RESIDUAL >= 2, others >= 0. */
+    int32_t slab_halo, slab_row0, slab_H_global;
+    int32_t _pad;
+    dpde_view x0;              /* denoised estimate x_N (B,C,H,W), F32 or F64                             */
+    dpde_view dxdt;            /* its time derivative, same dtype; ptr NULL = zeros (X_and_dXdt_dummy)    */
+    dpde_view obs_a, mask_a;   /* (.., ch_a, H, W) broadcastable; obs F32/F64, mask U8/F32/F64            */
+    dpde_view obs_u, mask_u;   /* (.., C-ch_a, H, W)                                                      */
+    const double* sample_coef; /* HEAT: alpha_b = labels[b,-1] (B,);  LLG_RESIDUAL: h_ext in A/m (B,3)    */
+    double dx;                 /* grid spacing (square cells, sample.py:133)                              */
+    double w_a, w_u, w_pde;    /* guidance weights of this step (sample.py:348-351)                       */
+    /* LLG residual constants (tests/test_llg_pde_loss.py:36-41): r = dmdt - tau (-gamma m x H - alpha m x (m x H)),
+       H = h_ext + c_ex lap(m) + c_an (m . e) e */
+    double gamma, alpha, c_ex, c_an, tau;
+    double easy_axis[3];
+} dpde_guidance_desc;
+
+/* scalars[8] written by reduce/finalize: loss_a, loss_u, loss_pde, loss_comb, then the three seed coefficients
+   c_a = w_a/loss_a, c_u = w_u/loss_u, c_pde (kind dependent), and one spare. */
+#define DPDE_NUM_SCALARS 8
+
+int dpde_abi_version(void);
+const char* dpde_last_error(void);
+
+/* Bytes of scratch the reduce pass needs (per-CTA partial sums + a ticket counter).  The caller zero-fills it
+   once after allocation; the library leaves it zeroed-where-needed after every call. */
+size_t dpde_guidance_workspace_bytes(void);
+
+/* Pass 1 -- the three global sums of sample.py:340-342 and of loss_fn (pde_losses.py:94,116):
+   sums[0] = sum (mask_a (a - obs_a))^2, sums[1] = same for u, sums[2] = sum r^2 (HEAT, LLG_RESIDUAL) or
+   sum (1-|m|)^2 (LLG_NORM).  With finalize != 0 the last CTA also runs dpde_guidance_finalize's arithmetic. */
+int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize,
+                         double* scalars, float* trace_row, dpde_stream_t stream);
+
+/* sums -> losses, loss_comb (sample.py:353) and seed coefficients; trace_row (4 floats, may be NULL) receives
+   [loss_a, loss_u, loss_pde, loss_comb] as sample.py:357 stores them.  Separate entry point so a multi-GPU caller
+   can all-reduce `sums` first (batch-coupled semantics / row slabs). */
+int dpde_guidance_finalize(const dpde_guidance_desc* desc, const double* sums, double* scalars, float* trace_row,
+                           dpde_stream_t stream);
+
+/* Pass 2 -- analytic vector-Jacobian product replacing autograd through sample.py:336-353:
+   g_x0 (B,C,H,W contiguous, dtype of x0) = d loss_comb / d x_N;  g_dxdt (same shape, may be NULL) = d / d dxdt.
+   `upstream` (device double, may be NULL) multiplies both -- the grad_output of a stand-alone loss. */
+int dpde_guidance_vjp(const dpde_guidance_desc* desc, const double* scalars, const double* upstream, void* g_x0,
+                      void* g_dxdt, dpde_stream_t stream);
+
+/* laplacian(u, dx), sample.py:106-134, on `planes` (H,W) images (adjoint != 0: its transpose, used as backward). */
+int dpde_laplacian(const void* u, void* out, int32_t dtype, int64_t planes, int32_t H, int32_t W,
+                   int64_t plane_stride_in, double dx, int32_t adjoint, dpde_stream_t stream);
+
+/* x = latents * sigma_0 (sample.py:316); also emits the fp32 copy the denoiser reads (sample.py:324). */
+int dpde_sampler_init(const double* latents, double sigma0, double* x64, float* x32, int64_t n, dpde_stream_t stream);
+
+/* Euler predictor, sample.py:327-328: x_eu = x_cur + (s_next - s_cur) (x_cur - x0_cur)/s_cur, emitted in fp32 for
+   the second denoiser evaluation (sample.py:331). */
+int dpde_euler_predict(const double* x_cur, const float* x0_cur, double sigma_cur, double sigma_next, float* x_eu32,
+                       int64_t n, dpde_stream_t stream);
+
+/* Backward of the predictor w.r.t. x0_cur: seed = fp32( -((s_next - s_cur) g_eu) / s_cur ). */
+int dpde_euler_predict_bwd(const float* g_eu32, double sigma_cur, double sigma_next, float* seed32, int64_t n,
+                           dpde_stream_t stream);
+
+/* Heun correction + guidance update, sample.py:330-334,355, fused:
+     x_next = x_cur + h (d_cur/2 + d_prime/2) - [ g_eu + (h g_eu)/s_cur + g_cur ],   h = s_next - s_cur
+   x0_next == NULL selects the last step (Euler only, sample.py:330).  g_eu / g_cur are the fp32 gradients the
+   denoiser backward produced at x_eu and x_cur (either may be NULL = 0).  Writes the fp64 state and its fp32 copy. */
+int dpde_heun_guided_update(const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
+                            const float* g_cur, double sigma_cur, double sigma_next, double* x_next64, float* x_next32,
+                            int64_t n, dpde_stream_t stream);
+
+/* Row-slab halo staging for `planes` local images of H_local rows (ghost rows included), W columns.
+   pack:   owned rows [halo, 2 halo) -> send_up, owned rows [H_local - 2 halo, H_local - halo) -> send_down
+   unpack: recv_up -> ghost rows [0, halo),      recv_down -> ghost rows [H_local - halo, H_local)
+   Each staging buffer holds planes * halo * W elements; a NULL buffer skips that side (grid boundary). */
+int dpde_halo_pack(const void* field, int32_t dtype, int64_t planes, int32_t H_local, int32_t W, int32_t halo,
+                   void* send_up, void* send_down, dpde_stream_t stream);
+int dpde_halo_unpack(void* field, int32_t dtype, int64_t planes, int32_t H_local, int32_t W, int32_t halo,
+                     const void* recv_up, const void* recv_down, dpde_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPDE_B200_H */

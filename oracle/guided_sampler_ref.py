@@ -353,3 +353,15 @@ def llg_residual_guidance_numpy(m, dmdt, field_mT, dx, consts: LLGConstants = LL
     if consts.K0 != 0.0:
         gm = gm + consts.c_an * (G_H * e).sum(axis=1, keepdims=True) * e
     return loss, -consts.tau * gm, g
+
+
+def X_and_dXdt(net, x, sigma, labels):
+    """Forward-mode time derivative in labels[:, 0] (sample.py:69-103)."""
+    t0 = labels[:, 0]
+
+    def f(t):
+        lbl = labels.clone()
+        lbl[:, 0] = t
+        return net(x, sigma, lbl)
+
+    return torch.func.jvp(f, (t0,), (torch.ones_like(t0),))
