@@ -86,9 +86,20 @@ def check(rc: int) -> None:
 
 # number of kernels this process launched through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0
+# when set to a list, every launch is bracketed by CUDA events on the current stream: (name, start, stop)
+event_log = None
 
 
 def call(name: str, *args) -> None:
     global launch_count
-    check(getattr(lib(), name)(*args))
+    if event_log is None:
+        check(getattr(lib(), name)(*args))
+    else:
+        import torch
+
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(getattr(lib(), name)(*args))
+        b.record()
+        event_log.append((name, a, b))
     launch_count += 1

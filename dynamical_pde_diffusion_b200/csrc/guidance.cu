@@ -93,6 +93,14 @@ __device__ __forceinline__ void cross3(const double* a, const double* b, double*
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+// Is the residual at local row y / column x defined and needed?  Rows ylo-1 .. yhi feed the transposed stencil of
+// the owned rows [ylo, yhi); the row must exist in the global grid (and therefore, with >= 2 ghost rows, its
+// vertical neighbours exist in the local buffer).
+__device__ __forceinline__ bool residual_needed(const Params& p, int y, int x) {
+    const int gy = y + p.yg0;
+    return y >= p.ylo - 1 && y <= p.yhi && gy >= 0 && gy < p.Hg && x >= 0 && x < p.W;
+}
+
 // heat residual r = dudt - alpha * lap(u)   (pde_losses.py:91-94)
 template <typename T>
 __device__ __forceinline__ double heat_residual(const Params& p, const T* __restrict__ u, const T* __restrict__ dudt,
@@ -371,7 +379,7 @@ guidance_vjp_kernel(const __grid_constant__ Params p, const double* __restrict__
                     const int y = tc.y0 + ly, x = tc.x0 + lx;
                     double r = 0.0;
                     uc[k] = 0.0;
-                    if (y < p.yhi && x < p.W) r = heat_residual(p, u, du, alpha, y, x, uc[k]);
+                    if (residual_needed(p, y, x)) r = heat_residual(p, u, du, alpha, y, x, uc[k]);
                     stage[(ly + 1) * SW + lx + 1] = r;
                 }
                 const int ring = 2 * SW + 2 * p.tile_h;
@@ -380,7 +388,7 @@ guidance_vjp_kernel(const __grid_constant__ Params p, const double* __restrict__
                     ring_coord(e, p.tile_h, p.tile_w, ry, rx);
                     const int y = tc.y0 + ry, x = tc.x0 + rx;
                     double r = 0.0, dummy;
-                    if (y >= 0 && y < p.H && y + p.yg0 >= 0 && y + p.yg0 < p.Hg && x >= 0 && x < p.W) r = heat_residual(p, u, du, alpha, y, x, dummy);
+                    if (residual_needed(p, y, x)) r = heat_residual(p, u, du, alpha, y, x, dummy);
                     stage[(ry + 1) * SW + rx + 1] = r;
                 }
                 __syncthreads();
@@ -456,7 +464,8 @@ guidance_vjp_kernel(const __grid_constant__ Params p, const double* __restrict__
                 const int y = tc.y0 + ly, x = tc.x0 + lx;
                 double GH[3] = {0.0, 0.0, 0.0};
                 local[k][0] = local[k][1] = local[k][2] = 0.0;
-                if (y < p.yhi && x < p.W) {
+                if (residual_needed(p, y, x)) {
+                    const bool owned = y < p.yhi;
                     const int64_t pix = (int64_t)y * p.W + x;
                     LLGPoint q;
                     llg_point(p, m0, p.x0.sc, d0, p.dxdt.sc, hext, y, x, q);
@@ -476,13 +485,13 @@ guidance_vjp_kernel(const __grid_constant__ Params p, const double* __restrict__
                     for (int c = 0; c < 3; ++c) {
                         const double Gm = -p.gamma * Hs[c] - p.alpha * (as[c] + Hq[c]);
                         double v = -p.tau * (Gm + p.c_an * eG * p.e[c]);
-                        if (p.has_u) {
+                        if (p.has_u && owned) {
                             double m;
                             const double d = masked_diff(p.obs_u, p.mask_u, tc.b, c, pix, q.m[c], m);
                             v += c_u * (m * d);
                         }
                         local[k][c] = v;
-                        if (gd) gd[c * plane + pix] = (T)s[c];
+                        if (gd && owned) gd[c * plane + pix] = (T)s[c];
                     }
                 }
 #pragma unroll
@@ -494,7 +503,7 @@ guidance_vjp_kernel(const __grid_constant__ Params p, const double* __restrict__
                 ring_coord(e, p.tile_h, p.tile_w, ry, rx);
                 const int y = tc.y0 + ry, x = tc.x0 + rx;
                 double GH[3] = {0.0, 0.0, 0.0};
-                if (y >= 0 && y < p.H && y + p.yg0 >= 0 && y + p.yg0 < p.Hg && x >= 0 && x < p.W) {
+                if (residual_needed(p, y, x)) {
                     LLGPoint q;
                     llg_point(p, m0, p.x0.sc, d0, p.dxdt.sc, hext, y, x, q);
                     double s[3] = {c_p * q.r[0], c_p * q.r[1], c_p * q.r[2]}, qq[3], qm[3];

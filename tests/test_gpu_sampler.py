@@ -12,14 +12,24 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True)
 def _ieee_fp32():
-    """Parity runs use IEEE fp32 convolutions (the reference's sampling_context opts into TF32, sample.py:626-630;
-    that is a throughput setting, exercised by bench.py, not a parity setting)."""
-    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    """Parity runs use IEEE fp32, deterministic cuDNN algorithms.
+
+    TF32 (the reference's sampling_context, sample.py:626-630) is a throughput setting exercised by bench.py.
+    Determinism matters: with cuDNN's default (atomics-based) backward kernels the ORACLE ITSELF differs run to run
+    by 1e-6..1e-4 per step on this network (scripts/step_parity_probe.py; the finite-difference time derivative
+    with eps = 1e-5 in fp32 amplifies one-ulp differences), with deterministic algorithms our sampler and the
+    oracle agree bit for bit at every step."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark,
+           torch.backends.cudnn.deterministic)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    torch.use_deterministic_algorithms(True, warn_only=True)
     yield
-    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    torch.use_deterministic_algorithms(False)
+    (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark,
+     torch.backends.cudnn.deterministic) = old
 
 
 def _dev():
