@@ -20,7 +20,7 @@ NUM_SCALARS = 8
 EXPORTED = (
     "dpde_abi_version", "dpde_last_error", "dpde_guidance_workspace_bytes", "dpde_guidance_reduce",
     "dpde_guidance_finalize", "dpde_guidance_vjp", "dpde_laplacian", "dpde_sampler_init", "dpde_euler_predict",
-    "dpde_euler_predict_bwd", "dpde_heun_guided_update", "dpde_halo_pack", "dpde_halo_unpack",
+    "dpde_euler_predict_bwd", "dpde_heun_guided_update", "dpde_halo_pack", "dpde_halo_unpack", "dpde_set_fast_path",
 )
 
 
@@ -71,6 +71,7 @@ def lib():
     L.dpde_heun_guided_update.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, i64, vp]
     L.dpde_halo_pack.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.dpde_halo_unpack.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
+    L.dpde_set_fast_path.argtypes = [C.c_int]
     for name in EXPORTED:
         fn = getattr(L, name)
         if name not in ("dpde_abi_version", "dpde_last_error", "dpde_guidance_workspace_bytes"):

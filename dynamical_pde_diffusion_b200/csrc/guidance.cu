@@ -565,9 +565,67 @@ laplacian_kernel(const T* __restrict__ u, T* __restrict__ out, int64_t planes, i
     }
 }
 
+#include "heat_march.cuh"
+
 // =========================================================================================================
 // host side
 // =========================================================================================================
+bool g_fast_path = true;
+
+inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
+
+// Can the row-marching kernels take this problem?  (else the generic tile kernels run)
+bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
+    if (!g_fast_path || p.kind != DPDE_PDE_HEAT || p.x0.dtype != DPDE_F32 || p.W % 4 != 0) return false;
+    if (!al(p.x0.p, 16) || !s4(p.x0)) return false;
+    if (p.dxdt.p && (!al(p.dxdt.p, 16) || !s4(p.dxdt))) return false;
+    if (g_x0 && !al(g_x0, 16)) return false;
+    if (g_dxdt && !al(g_dxdt, 16)) return false;
+    if (p.has_a && (p.obs_a.dtype != DPDE_F32 || p.mask_a.dtype != DPDE_U8 || !al(p.obs_a.p, 16) || !al(p.mask_a.p, 4) ||
+                    !s4(p.obs_a) || !s4(p.mask_a))) return false;
+    if (p.has_u && (p.obs_u.dtype != DPDE_F32 || p.mask_u.dtype != DPDE_U8 || !al(p.obs_u.p, 16) || !al(p.mask_u.p, 4) ||
+                    !s4(p.obs_u) || !s4(p.mask_u))) return false;
+    return true;
+}
+
+MarchGeom march_geometry(const Params& p) {
+    MarchGeom g;
+    const int rows = p.yhi - p.ylo;
+    if (p.W <= 128) {
+        int lw = 1, l2 = 0;
+        while (lw * 4 < p.W) { lw <<= 1; ++l2; }
+        g.lw_log2 = l2; g.segs_per_warp = 32 / lw; g.strips = 1; g.strip_w = p.W; g.halo_lane = 0;
+    } else {
+        g.lw_log2 = 5; g.segs_per_warp = 1; g.strip_w = 120; g.strips = (p.W + 119) / 120; g.halo_lane = 1;
+    }
+    // rows per chunk: long chunks amortise the 2-row warm-up, short ones expose more warps on small problems
+    const int64_t per_row_items = (int64_t)g.strips * p.n_u_units * p.B;
+    const int64_t want_warps = (int64_t)sm_count() * 16;
+    int R = 32;
+    while (R > 8 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
+    g.R = R;
+    g.chunks = (rows + R - 1) / R;
+    g.n_seg_items = (int64_t)g.chunks * per_row_items;
+    g.n_warp_items = (g.n_seg_items + g.segs_per_warp - 1) / g.segs_per_warp;
+    g.a_plane4 = (int64_t)rows * p.W / 4;
+    g.a_total4 = g.a_plane4 * p.ch_a * p.B;
+    return g;
+}
+
+template <typename K>
+int march_grid(K kernel, const MarchGeom& g) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    int64_t need = (g.n_warp_items + kThreads / 32 - 1) / (kThreads / 32);
+    const int64_t need_a = (g.a_total4 + kThreads - 1) / kThreads;
+    if (need_a > need) need = need_a;
+    int64_t grid = (int64_t)sm_count() * occ;
+    if (grid > need) grid = need;
+    if (grid > kMaxPartials) grid = kMaxPartials;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
 View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }
 
 int validate_and_fill(const dpde_guidance_desc* d, int tile_pix, Params& p, const char* who) {
@@ -686,6 +744,12 @@ using namespace dpde;
 
 extern "C" {
 
+int dpde_set_fast_path(int enable) {
+    const int old = g_fast_path ? 1 : 0;
+    g_fast_path = enable != 0;
+    return old;
+}
+
 size_t dpde_guidance_workspace_bytes(void) { return (size_t)(3 * kMaxPartials + 2) * sizeof(double); }
 
 int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize, double* scalars,
@@ -697,6 +761,12 @@ int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double
     double* partials = reinterpret_cast<double*>(workspace);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + 3 * kMaxPartials);
     cudaStream_t s = (cudaStream_t)stream;
+    if (march_eligible(p, nullptr, nullptr)) {
+        const MarchGeom g = march_geometry(p);
+        heat_march_reduce_kernel<<<march_grid(heat_march_reduce_kernel, g), kThreads, 0, s>>>(p, g, partials, ticket, sums,
+                                                                                              finalize, scalars, trace_row);
+        return check_launch("dpde_guidance_reduce (march)");
+    }
     return p.x0.dtype == DPDE_F32 ? launch_reduce<float>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
                                   : launch_reduce<double>(p, partials, ticket, sums, finalize, scalars, trace_row, s);
 }
@@ -716,6 +786,12 @@ int dpde_guidance_vjp(const dpde_guidance_desc* desc, const double* scalars, con
     if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, "dpde_guidance_vjp")) return rc;
     if (!scalars || !g_x0) return fail(DPDE_ERR_INVALID, "dpde_guidance_vjp: scalars/g_x0 is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    if (march_eligible(p, g_x0, g_dxdt)) {
+        const MarchGeom g = march_geometry(p);
+        heat_march_vjp_kernel<<<march_grid(heat_march_vjp_kernel, g), kThreads, 0, s>>>(p, g, scalars, upstream, (float*)g_x0,
+                                                                                        (float*)g_dxdt);
+        return check_launch("dpde_guidance_vjp (march)");
+    }
     return p.x0.dtype == DPDE_F32 ? launch_vjp<float>(p, scalars, upstream, g_x0, g_dxdt, s)
                                   : launch_vjp<double>(p, scalars, upstream, g_x0, g_dxdt, s);
 }

@@ -82,6 +82,11 @@ typedef struct dpde_guidance_desc {
 int dpde_abi_version(void);
 const char* dpde_last_error(void);
 
+/* Kernel selection: 1 (default) lets eligible problems (fp32 fields, W % 4 == 0, 16-byte aligned operands, fp32
+   observations, uint8 masks) take the register row-marching kernels; 0 forces the generic tile kernels, which accept
+   every layout.  Both give the same results (tests run both).  Returns the previous setting. */
+int dpde_set_fast_path(int enable);
+
 /* Bytes of scratch the reduce pass needs (per-CTA partial sums + a ticket counter).  The caller zero-fills it
    once after allocation; the library leaves it zeroed-where-needed after every call. */
 size_t dpde_guidance_workspace_bytes(void);

@@ -133,10 +133,22 @@ def _heat_case(B, ch_a, cu, H, W, seed, mask_mode="hw", dtype=torch.float32):
     return x0, dxdt, labels, obs_a, obs_u, mask_a, mask_u
 
 
+@pytest.fixture(params=["march", "generic"])
+def kernel_path(request):
+    """Run a test once with the register row-marching kernels enabled (taken when the layout is eligible) and once
+    with the generic tile kernels forced."""
+    from dynamical_pde_diffusion_b200 import _ffi
+
+    old = _ffi.lib().dpde_set_fast_path(1 if request.param == "march" else 0)
+    yield request.param
+    _ffi.lib().dpde_set_fast_path(old)
+
+
 @pytest.mark.parametrize("shape", [(3, 1, 1, 12, 10), (2, 1, 1, 2, 2), (2, 1, 1, 64, 64), (1, 1, 1, 37, 130), (2, 1, 1, 130, 17),
-                                   (4, 1, 1, 128, 128), (1, 2, 2, 33, 65), (2, 0, 1, 16, 16)])
+                                   (4, 1, 1, 128, 128), (1, 2, 2, 33, 65), (2, 0, 1, 16, 16), (1, 1, 1, 40, 256),
+                                   (1, 1, 1, 24, 520), (3, 1, 1, 9, 16), (2, 1, 1, 5, 8), (1, 1, 1, 3, 4), (2, 2, 2, 70, 132)])
 @pytest.mark.parametrize("mask_mode", ["hw", "chw", "full"])
-def test_heat_guidance_matches_closed_form(shape, mask_mode):
+def test_heat_guidance_matches_closed_form(shape, mask_mode, kernel_path):
     from dynamical_pde_diffusion_b200 import GuidanceEngine
     from dynamical_pde_diffusion_b200._ffi import PDE_HEAT
 
@@ -185,7 +197,7 @@ def test_heat_guidance_fp64_fields_and_autograd_cross_check():
     _close(eng.scalars[:3], torch.stack([la.reshape(()), lu.reshape(()), lp.reshape(())]), 1e-12, "losses")
 
 
-def test_empty_mask_branches_and_nan_semantics():
+def test_empty_mask_branches_and_nan_semantics(kernel_path):
     """mask.sum() == 0 -> the loss is the constant 0 with no gradient (sample.py:337-342);
     a non-empty mask with zero residual -> NaN gradient, as sqrt'(0) gives in the reference."""
     from dynamical_pde_diffusion_b200 import GuidanceEngine
@@ -291,7 +303,7 @@ def test_level1_llg_residual_matches_oracle_autograd():
 # ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind_name", ["heat", "llg_residual", "llg_norm"])
 @pytest.mark.parametrize("n_slabs", [2, 3])
-def test_row_slab_decomposition_equals_whole_grid(kind_name, n_slabs):
+def test_row_slab_decomposition_equals_whole_grid(kind_name, n_slabs, kernel_path):
     from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants
     from dynamical_pde_diffusion_b200._ffi import PDE_HEAT, PDE_LLG_NORM, PDE_LLG_RESIDUAL
 
