@@ -578,6 +578,7 @@ inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
 // Can the row-marching kernels take this problem?  (else the generic tile kernels run)
 bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
     if (!g_fast_path || p.kind != DPDE_PDE_HEAT || p.x0.dtype != DPDE_F32 || p.W % 4 != 0) return false;
+    if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * ((p.H + 7) / 8) * ((p.W + 119) / 120) >= (1ll << 30)) return false;
     if (!al(p.x0.p, 16) || !s4(p.x0)) return false;
     if (p.dxdt.p && (!al(p.dxdt.p, 16) || !s4(p.dxdt))) return false;
     if (g_x0 && !al(g_x0, 16)) return false;
@@ -606,24 +607,49 @@ MarchGeom march_geometry(const Params& p) {
     while (R > 8 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
     g.R = R;
     g.chunks = (rows + R - 1) / R;
-    g.n_seg_items = (int64_t)g.chunks * per_row_items;
+    g.n_seg_items = (int)((int64_t)g.chunks * per_row_items);
     g.n_warp_items = (g.n_seg_items + g.segs_per_warp - 1) / g.segs_per_warp;
-    g.a_plane4 = (int64_t)rows * p.W / 4;
-    g.a_total4 = g.a_plane4 * p.ch_a * p.B;
+    g.a_plane4 = (int)((int64_t)rows * p.W / 4);
+    g.a_blocks_per_plane = (g.a_plane4 + kABlock - 1) / kABlock;
+    g.n_a_items = g.a_blocks_per_plane * p.ch_a * p.B;
     return g;
 }
 
 template <typename K>
 int march_grid(K kernel, const MarchGeom& g) {
+    // opt in to > 48 KB dynamic shared memory once per kernel instantiation, then size a persistent grid
+    static thread_local const void* configured[16] = {nullptr};
+    bool seen = false;
+    for (const void* k : configured) seen = seen || k == (const void*)kernel;
+    if (!seen) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+        for (auto& k : configured)
+            if (!k) { k = (const void*)kernel; break; }
+    }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
-    int64_t need = (g.n_warp_items + kThreads / 32 - 1) / (kThreads / 32);
-    const int64_t need_a = (g.a_total4 + kThreads - 1) / kThreads;
-    if (need_a > need) need = need_a;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, kRingBytes) != cudaSuccess || occ < 1) occ = 1;
+    int64_t need = ((int64_t)g.n_warp_items + g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
     int64_t grid = (int64_t)sm_count() * occ;
     if (grid > need) grid = need;
     if (grid > kMaxPartials) grid = kMaxPartials;
     return (int)(grid < 1 ? 1 : grid);
+}
+
+template <bool HAS_D, bool HAS_O>
+int launch_march_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal,
+                        float* trace, cudaStream_t s) {
+    const MarchGeom g = march_geometry(p);
+    auto k = heat_march_reduce_kernel<HAS_D, HAS_O>;
+    k<<<march_grid(k, g), kThreads, kRingBytes, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    return check_launch("dpde_guidance_reduce (march)");
+}
+
+template <bool HAS_D, bool HAS_O>
+int launch_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
+    const MarchGeom g = march_geometry(p);
+    auto k = heat_march_vjp_kernel<HAS_D, HAS_O>;
+    k<<<march_grid(k, g), kThreads, kRingBytes, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    return check_launch("dpde_guidance_vjp (march)");
 }
 
 View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }
@@ -762,10 +788,11 @@ int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double
     unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + 3 * kMaxPartials);
     cudaStream_t s = (cudaStream_t)stream;
     if (march_eligible(p, nullptr, nullptr)) {
-        const MarchGeom g = march_geometry(p);
-        heat_march_reduce_kernel<<<march_grid(heat_march_reduce_kernel, g), kThreads, 0, s>>>(p, g, partials, ticket, sums,
-                                                                                              finalize, scalars, trace_row);
-        return check_launch("dpde_guidance_reduce (march)");
+        const bool d = p.dxdt.p != nullptr, o = p.has_u != 0;
+        return d ? (o ? launch_march_reduce<true, true>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
+                      : launch_march_reduce<true, false>(p, partials, ticket, sums, finalize, scalars, trace_row, s))
+                 : (o ? launch_march_reduce<false, true>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
+                      : launch_march_reduce<false, false>(p, partials, ticket, sums, finalize, scalars, trace_row, s));
     }
     return p.x0.dtype == DPDE_F32 ? launch_reduce<float>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
                                   : launch_reduce<double>(p, partials, ticket, sums, finalize, scalars, trace_row, s);
@@ -787,10 +814,10 @@ int dpde_guidance_vjp(const dpde_guidance_desc* desc, const double* scalars, con
     if (!scalars || !g_x0) return fail(DPDE_ERR_INVALID, "dpde_guidance_vjp: scalars/g_x0 is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     if (march_eligible(p, g_x0, g_dxdt)) {
-        const MarchGeom g = march_geometry(p);
-        heat_march_vjp_kernel<<<march_grid(heat_march_vjp_kernel, g), kThreads, 0, s>>>(p, g, scalars, upstream, (float*)g_x0,
-                                                                                        (float*)g_dxdt);
-        return check_launch("dpde_guidance_vjp (march)");
+        const bool d = p.dxdt.p != nullptr, o = p.has_u != 0;
+        float *gx = (float*)g_x0, *gd = (float*)g_dxdt;
+        return d ? (o ? launch_march_vjp<true, true>(p, scalars, upstream, gx, gd, s) : launch_march_vjp<true, false>(p, scalars, upstream, gx, gd, s))
+                 : (o ? launch_march_vjp<false, true>(p, scalars, upstream, gx, gd, s) : launch_march_vjp<false, false>(p, scalars, upstream, gx, gd, s));
     }
     return p.x0.dtype == DPDE_F32 ? launch_vjp<float>(p, scalars, upstream, g_x0, g_dxdt, s)
                                   : launch_vjp<double>(p, scalars, upstream, g_x0, g_dxdt, s);

@@ -8,8 +8,16 @@
 //   * every field row is read once from HBM as a coalesced 512-byte warp access (LDG.128), the vertical stencil
 //     neighbours live in registers (three-row window of u, three-row window of the residual r);
 //   * horizontal neighbours come from the adjacent lane by __shfl (u: 2 shuffles per row, r: 2 double shuffles);
-//   * the next row's loads are issued before the current row's arithmetic (software prefetch), all loads are
-//     unconditional (row / column indices are clamped, results of invalid lanes are zeroed afterwards);
+//   * rows are prefetched with cp.async (LDGSTS) into a per-lane shared-memory ring of kRing (8) row elements:
+//     each lane copies its own 16 bytes and reads only its own slots back, so no barrier is needed and prefetch
+//     depth costs no registers (Little's law: ~50 KB must be in flight per SM to cover HBM latency at 6.5 TB/s;
+//     16 warps x 3-4 rows x 52 B x 32 lanes = 80-106 KB).  One ring element holds u, dudt, obs and mask of the SAME
+//     row, so one row-offset computation serves four copies; consumers read the three fields from elements
+//     it+2 / it+1 / it.  Row indices outside the grid are REFLECTED (u[-1] = u[1]), which is exactly the
+//     reference's padding, so the stencil needs no boundary selects; column indices of idle lanes are clamped and
+//     their results multiplied by zero;
+//   * the three-row windows are kept in fp64, so every loaded value is converted once (F2F.F64.F32 issues at a
+//     quarter of the DFMA rate) and the uint8 mask is widened with the 2^52 trick (one DADD, no I2F);
 //   * grids wider than 128 columns are cut into strips of 120 output columns + one halo lane on each side
 //     (halo reads hit L2); narrow grids pack several row segments into one warp (W = 64: two, W = 16: eight).
 // A lane spends ~30 instructions per pixel; arithmetic and accumulation stay fp64 (see guidance.cu header).
@@ -19,133 +27,254 @@
 
 struct MarchGeom {
     int lw_log2, segs_per_warp, strips, strip_w, halo_lane, R, chunks;
-    int64_t n_seg_items, n_warp_items;
-    int64_t a_total4, a_plane4;  // float4 count over all a-planes (owned rows) and per plane
+    int n_seg_items, n_warp_items;       // u-plane work: row segments, and warps' worth of them
+    int a_blocks_per_plane, n_a_items;   // a-plane work: blocks of kABlock float4 within one plane's owned rows
+    int a_plane4;                        // float4 per a-plane (owned rows)
 };
+
+constexpr int kABlock = 1024;            // float4 per a-plane work item (4096 pixels)
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uchar4 ldg4(const unsigned char* p) { return __ldg(reinterpret_cast<const uchar4*>(p)); }
+
+constexpr int kRing = 8;                                            // ring elements (rows) per lane, power of two
+constexpr int kRingBytes = kRing * kThreads * (3 * 16 + 4);         // dynamic shared memory per CTA (106496 B)
+
+// shared-memory operands are 32-bit shared-window addresses computed once per thread (the generic->shared
+// conversion otherwise costs ~6 instructions per copy)
+__device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned smem) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned smem) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// exact uint8 -> double without the (quarter-rate) I2F.F64: 2^52 + k has k in its low mantissa bits
+__device__ __forceinline__ double u8_to_double(unsigned k) { return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0; }
+
+struct D4v {
+    double v[4];
+};
+__device__ __forceinline__ D4v widen(const float4& f) { return D4v{{(double)f.x, (double)f.y, (double)f.z, (double)f.w}}; }
 
 struct MarchLane {
     int b, cu, col0, ys, ye;
     bool lane_ok, out_ok, left_edge, right_edge;
 };
 
-__device__ __forceinline__ MarchLane march_decode(const Params& p, const MarchGeom& g, int64_t wi, int lane) {
+__device__ __forceinline__ MarchLane march_decode(const Params& p, const MarchGeom& g, int wi, int lane) {
     const int LW = 1 << g.lw_log2, seg = lane >> g.lw_log2, l = lane & (LW - 1);
-    int64_t si = wi * g.segs_per_warp + seg;
-    const bool seg_ok = si < g.n_seg_items;
+    unsigned si = (unsigned)wi * g.segs_per_warp + seg;
+    const bool seg_ok = si < (unsigned)g.n_seg_items;
     if (!seg_ok) si = g.n_seg_items - 1;
     MarchLane m;
-    m.b = (int)(si % p.B);
-    int64_t t = si / p.B;
-    m.cu = (int)(t % p.n_u_units);
-    t /= p.n_u_units;
-    const int strip = (int)(t % g.strips), chunk = (int)(t / g.strips);
+    unsigned t = si / (unsigned)p.B;
+    m.b = (int)(si - t * p.B);
+    unsigned t2 = t / (unsigned)p.n_u_units;
+    m.cu = (int)(t - t2 * p.n_u_units);
+    const unsigned chunk = t2 / (unsigned)g.strips;
+    const int strip = (int)(t2 - chunk * g.strips);
     m.col0 = strip * g.strip_w - 4 * g.halo_lane + 4 * l;
     m.lane_ok = seg_ok && m.col0 >= 0 && m.col0 < p.W;
     m.out_ok = m.lane_ok && m.col0 >= strip * g.strip_w && m.col0 < (strip + 1) * g.strip_w;
     m.left_edge = (m.col0 == 0);
     m.right_edge = (m.col0 + 4 == p.W);
-    m.ys = p.ylo + chunk * g.R;
+    m.ys = p.ylo + (int)chunk * g.R;
     m.ye = min(m.ys + g.R, p.yhi);
     return m;
 }
 
-// residual of one row for the lane's four columns: r = dudt - a_s * (up + down + left + right - 4 centre)
-__device__ __forceinline__ void heat_row_residual(const float4& up, const float4& c, const float4& dn, float lf, float rt,
-                                                  const float4& dt, double a_s, bool ok, double* r) {
-    const double c0 = c.x, c1 = c.y, c2 = c.z, c3 = c.w;
-    const double s0 = (((double)up.x + (double)dn.x) + ((double)lf + c1)) - 4.0 * c0;
-    const double s1 = (((double)up.y + (double)dn.y) + (c0 + c2)) - 4.0 * c1;
-    const double s2 = (((double)up.z + (double)dn.z) + (c1 + c3)) - 4.0 * c2;
-    const double s3 = (((double)up.w + (double)dn.w) + (c2 + (double)rt)) - 4.0 * c3;
-    r[0] = ok ? (double)dt.x - a_s * s0 : 0.0;
-    r[1] = ok ? (double)dt.y - a_s * s1 : 0.0;
-    r[2] = ok ? (double)dt.z - a_s * s2 : 0.0;
-    r[3] = ok ? (double)dt.w - a_s * s3 : 0.0;
+// Local buffer offset (in elements) of row y, with the reference's reflect padding applied in GLOBAL row numbers:
+// rows above the grid mirror about row 0, rows below about row Hg-1 (sample.py:132).  Clamped into the buffer.
+__device__ __forceinline__ int row_offset(const Params& p, int y) {
+    int gy = y + p.yg0;
+    gy = gy < 0 ? -gy : gy;
+    gy = gy > p.Hg - 1 ? 2 * (p.Hg - 1) - gy : gy;
+    return min(max(gy - p.yg0, 0), p.H - 1) * p.W;
+}
+
+// Per-lane prefetch ring.  Element s holds u, dudt, obs and mask of row (row0 + s) for the lane's four columns.
+// HAS_D / HAS_O: dudt / observation operands present (compile-time, so the loop carries no pointer tests).
+template <bool HAS_D, bool HAS_O>
+struct RowRing {
+    unsigned su, sd, so, sm;                 // shared-window byte addresses of this lane's slot 0 in each field ring
+    const float *u, *du, *ob;
+    const unsigned char* mk;
+    int row0;
+
+    static __device__ __forceinline__ unsigned slot16(int s) { return (unsigned)(s & (kRing - 1)) * (kThreads * 16); }
+    static __device__ __forceinline__ unsigned slot4(int s) { return (unsigned)(s & (kRing - 1)) * (kThreads * 4); }
+
+    // start the copies of element s (fields selected by warp-uniform flags); always commits exactly one group
+    __device__ __forceinline__ void issue(const Params& p, int s, bool fu, bool fd, bool fo) const {
+        const int off = row_offset(p, row0 + s);
+        if (fu) cp_async16(su + slot16(s), u + off);
+        if (HAS_D && fd) cp_async16(sd + slot16(s), du + off);
+        if (HAS_O && fo) {
+            cp_async16(so + slot16(s), ob + off);
+            cp_async4(sm + slot4(s), mk + off);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ float4 get_u(int s) const { return lds128(su + slot16(s)); }
+    __device__ __forceinline__ float4 get_d(int s) const { return HAS_D ? lds128(sd + slot16(s)) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ float4 get_o(int s) const { return HAS_O ? lds128(so + slot16(s)) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ unsigned get_m(int s) const { return HAS_O ? lds32(sm + slot4(s)) : 0u; }
+
+    __device__ __forceinline__ void init(unsigned char* smem, int tid) {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
+        su = base + tid * 16;
+        sd = su + kRing * kThreads * 16;
+        so = sd + kRing * kThreads * 16;
+        sm = base + 3 * kRing * kThreads * 16 + tid * 4;
+    }
+    // Bind the lane's column pointers of one work item.
+    __device__ __forceinline__ void bind(const Params& p, const MarchLane& m, const float* x0, const float* dxp) {
+        const int colc = m.lane_ok ? m.col0 : 0, ch = p.ch_a + m.cu;
+        u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + colc;
+        du = HAS_D ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + colc : nullptr;
+        ob = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + colc : nullptr;
+        mk = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + colc : nullptr;
+    }
+};
+
+// unscaled 5-point sums of one row for the lane's four columns (rows already reflected by the loader)
+__device__ __forceinline__ void lap_row(const D4v& up, const D4v& c, const D4v& dn, double lf, double rt, double* s) {
+    s[0] = ((up.v[0] + dn.v[0]) + (lf + c.v[1])) - 4.0 * c.v[0];
+    s[1] = ((up.v[1] + dn.v[1]) + (c.v[0] + c.v[2])) - 4.0 * c.v[1];
+    s[2] = ((up.v[2] + dn.v[2]) + (c.v[1] + c.v[3])) - 4.0 * c.v[2];
+    s[3] = ((up.v[3] + dn.v[3]) + (c.v[2] + rt)) - 4.0 * c.v[3];
+}
+
+// a-plane work item -> (batch, channel, first float4 of the block inside the plane's owned rows, float4 count)
+struct AItem {
+    int b, ch, first4, n4;
+};
+__device__ __forceinline__ AItem a_decode(const Params& p, const MarchGeom& g, int item) {
+    // batch index innermost: the B samples of one block are processed back to back, so observation / mask
+    // operands that broadcast over the batch are fetched from HBM once and then hit in L2
+    const unsigned t = (unsigned)item / (unsigned)p.B;
+    AItem a;
+    a.b = (int)((unsigned)item - t * p.B);
+    const unsigned blk = t / (unsigned)p.ch_a;
+    a.ch = (int)(t - blk * p.ch_a);
+    a.first4 = (int)blk * kABlock;
+    a.n4 = min(kABlock, g.a_plane4 - a.first4);
+    return a;
+}
+
+// Each warp owns every nwarps-th u-item (compute/issue bound) and a-item (pure streaming, latency bound) and
+// alternates between the two kinds in proportion, odd warps starting with the other kind, so that at any time an
+// SM runs a mix of both and the streaming warps' memory stalls overlap the marching warps' arithmetic.
+template <typename FU, typename FA>
+__device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, int n_a, int a_first, FU&& do_u, FA&& do_a) {
+    const int nu_w = n_u > warp0 ? (n_u - warp0 + nwarps - 1) / nwarps : 0;
+    const int na_w = n_a > warp0 ? (n_a - warp0 + nwarps - 1) / nwarps : 0;
+    int ju = 0, ja = 0;
+    while (ju < nu_w || ja < na_w) {
+        const long long lhs = (long long)ju * na_w, rhs = (long long)ja * nu_w;
+        const bool take_u = ju < nu_w && (ja >= na_w || (a_first ? lhs < rhs : lhs <= rhs));
+        if (take_u) {
+            do_u(warp0 + ju * nwarps);
+            ++ju;
+        } else {
+            do_a(warp0 + ja * nwarps);
+            ++ja;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // pass 1 (fast): S_a, S_u, S_pde
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+template <bool HAS_D, bool HAS_O>
+__global__ void __launch_bounds__(kThreads, 2)
 heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g,
                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
                          int finalize, double* __restrict__ scal, float* __restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char ring_mem[];
     __shared__ double scratch[3 * (kThreads / 32)];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31;
     const float* x0 = reinterpret_cast<const float*>(p.x0.p);
     const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
+    const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
 
-    // ---- a-planes: sum (mask (a - obs))^2, pure float4 streaming over owned rows
-    if (p.has_a) {
-        const float* ob = reinterpret_cast<const float*>(p.obs_a.p);
-        const unsigned char* mk = reinterpret_cast<const unsigned char*>(p.mask_a.p);
-        for (int64_t i = (int64_t)blockIdx.x * kThreads + tid; i < g.a_total4; i += (int64_t)gridDim.x * kThreads) {
-            const int64_t pl = i / g.a_plane4, pix = (int64_t)p.ylo * p.W + 4 * (i - pl * g.a_plane4);
-            const int b = (int)(pl / p.ch_a), ch = (int)(pl - (int64_t)b * p.ch_a);
-            const float4 a = ldg4(x0 + (int64_t)b * p.x0.sb + (int64_t)ch * p.x0.sc + pix);
-            const float4 o = ldg4(ob + (int64_t)b * p.obs_a.sb + (int64_t)ch * p.obs_a.sc + pix);
-            const uchar4 m = ldg4(mk + (int64_t)b * p.mask_a.sb + (int64_t)ch * p.mask_a.sc + pix);
-            const double d0 = (double)m.x * ((double)a.x - (double)o.x), d1 = (double)m.y * ((double)a.y - (double)o.y);
-            const double d2 = (double)m.z * ((double)a.z - (double)o.z), d3 = (double)m.w * ((double)a.w - (double)o.w);
+    // ---- a-planes: sum (mask (a - obs))^2; a warp streams one block of a plane with 128-bit loads
+    auto do_a = [&](int item) {
+        const AItem a = a_decode(p, g, item);
+        const int base = p.ylo * p.W + 4 * a.first4;
+        const float* pa = x0 + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
+        const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
+        const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
+#pragma unroll 8
+        for (int i = lane; i < a.n4; i += 32) {
+            const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
+            const uchar4 m = ldg4(pm + 4 * i);
+            const double d0 = u8_to_double(m.x) * ((double)v.x - (double)o.x), d1 = u8_to_double(m.y) * ((double)v.y - (double)o.y);
+            const double d2 = u8_to_double(m.z) * ((double)v.z - (double)o.z), d3 = u8_to_double(m.w) * ((double)v.w - (double)o.w);
             s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
         }
-    }
+    };
 
-    // ---- u-planes: march down the rows
-    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    // ---- u-planes: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1].
+    //      Ring element s is row ys + s:  uc comes from element it+1, dudt / obs / mask from element it.
     const int LW = 1 << g.lw_log2;
-    for (int64_t wi = warp0; wi < g.n_warp_items; wi += nwarps) {
+    RowRing<HAS_D, HAS_O> ring;
+    ring.init(ring_mem, tid);
+    auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
-        const int colc = m.lane_ok ? m.col0 : 0, ch = p.ch_a + m.cu;
-        const float* u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + colc;
-        const float* du = dxp ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + colc : nullptr;
-        const float* ob = p.has_u ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + colc : nullptr;
-        const unsigned char* mk = p.has_u ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + colc : nullptr;
+        ring.bind(p, m, x0, dxp);
+        ring.row0 = m.ys;
+        const int n_it = g.R, n_el = g.R + 1;
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
         const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
-        const int rmax = p.H - 1;
-        auto row = [&](int y) { return (int64_t)min(max(y, 0), rmax) * p.W; };
-        float4 ua = ldg4(u + row(m.ys - 1)), ub = ldg4(u + row(m.ys));
-        float4 n_uc = ldg4(u + row(m.ys + 1));
-        float4 n_dt = du ? ldg4(du + row(m.ys)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 n_ob = make_float4(0.f, 0.f, 0.f, 0.f);
-        uchar4 n_mk = make_uchar4(0, 0, 0, 0);
-        if (p.has_u) {
-            n_ob = ldg4(ob + row(m.ys));
-            n_mk = ldg4(mk + row(m.ys));
-        }
-#pragma unroll 1
-        for (int it = 0; it < g.R; ++it) {
-            const int j = m.ys + it;
-            const float4 uc = n_uc, dt = n_dt, o = n_ob;
-            const uchar4 k = n_mk;
-            n_uc = ldg4(u + row(j + 2));                         // prefetch the next row's operands
-            if (du) n_dt = ldg4(du + row(j + 1));
-            if (p.has_u) {
-                n_ob = ldg4(ob + row(j + 1));
-                n_mk = ldg4(mk + row(j + 1));
-            }
-            const int gj = j + p.yg0;
-            float lf = __shfl_up_sync(0xffffffffu, ub.w, 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.x, 1, LW);
-            if (m.left_edge) lf = ub.y;                          // reflect: u[-1] = u[1]
-            if (m.right_edge) rt = ub.z;
-            const bool ok = m.out_ok && j < m.ye;
-            double r[4];
-            heat_row_residual(gj == 0 ? uc : ua, ub, gj == p.Hg - 1 ? ua : uc, lf, rt, dt, a_s, ok, r);
-            s_p += (r[0] * r[0] + r[1] * r[1]) + (r[2] * r[2] + r[3] * r[3]);
-            if (p.has_u && ok) {
-                const double d0 = (double)k.x * ((double)ub.x - (double)o.x), d1 = (double)k.y * ((double)ub.y - (double)o.y);
-                const double d2 = (double)k.z * ((double)ub.z - (double)o.z), d3 = (double)k.w * ((double)ub.w - (double)o.w);
+        D4v ua = widen(ldg4(ring.u + row_offset(p, m.ys - 1))), ub = widen(ldg4(ring.u + row_offset(p, m.ys)));
+#pragma unroll 3
+        for (int it = 0; it < n_it; ++it) {
+            cp_async_wait<kRing - 2>();                          // elements <= it + 1 have landed
+            const D4v uc = widen(ring.get_u(it + 1));
+            const float4 dt = ring.get_d(it), o = ring.get_o(it);
+            unsigned k = ring.get_m(it);
+            const int sn = it + kRing;                           // refill the slot just drained
+            ring.issue(p, sn, sn < n_el, sn < n_it, sn < n_it);
+            double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
+            if (m.left_edge) lf = ub.v[1];                       // reflect: u[-1] = u[1]
+            if (m.right_edge) rt = ub.v[2];
+            const bool ok = m.out_ok && m.ys + it < m.ye;
+            double s[4];
+            lap_row(ua, ub, uc, lf, rt, s);
+            const double r0 = (double)dt.x - a_s * s[0], r1 = (double)dt.y - a_s * s[1];
+            const double r2 = (double)dt.z - a_s * s[2], r3 = (double)dt.w - a_s * s[3];
+            const double okf = ok ? 1.0 : 0.0;
+            s_p += okf * ((r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3));
+            if (HAS_O) {
+                if (!ok) k = 0u;
+                const double d0 = u8_to_double(k & 255u) * (ub.v[0] - (double)o.x), d1 = u8_to_double((k >> 8) & 255u) * (ub.v[1] - (double)o.y);
+                const double d2 = u8_to_double((k >> 16) & 255u) * (ub.v[2] - (double)o.z), d3 = u8_to_double(k >> 24) * (ub.v[3] - (double)o.w);
                 s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
             }
             ua = ub;
             ub = uc;
         }
-    }
+        cp_async_wait<0>();
+    };
+    run_interleaved(warp0, nwarps, g.n_warp_items, p.has_a ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
 
     block_sum3(s_a, s_u, s_p, scratch);
     if (tid == 0) {
@@ -177,105 +306,111 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 (fast): seed gradient
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+template <bool HAS_D, bool HAS_O>
+__global__ void __launch_bounds__(kThreads, 2)
 heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, const double* __restrict__ scal,
                       const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    extern __shared__ __align__(16) unsigned char ring_mem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const double up = upstream ? __ldg(upstream) : 1.0;
     const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
     const float* x0 = reinterpret_cast<const float*>(p.x0.p);
     const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
     const int64_t plane = (int64_t)p.H * p.W;
+    const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
 
     // ---- a-planes: g = c_a mask (mask (a - obs)), zeros when the mask is empty (sample.py:337-342)
-    {
-        const float* ob = reinterpret_cast<const float*>(p.obs_a.p);
-        const unsigned char* mk = reinterpret_cast<const unsigned char*>(p.mask_a.p);
-        for (int64_t i = (int64_t)blockIdx.x * kThreads + tid; i < g.a_total4; i += (int64_t)gridDim.x * kThreads) {
-            const int64_t pl = i / g.a_plane4, pix = (int64_t)p.ylo * p.W + 4 * (i - pl * g.a_plane4);
-            const int b = (int)(pl / p.ch_a), ch = (int)(pl - (int64_t)b * p.ch_a);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.has_a) {
-                const float4 a = ldg4(x0 + (int64_t)b * p.x0.sb + (int64_t)ch * p.x0.sc + pix);
-                const float4 o = ldg4(ob + (int64_t)b * p.obs_a.sb + (int64_t)ch * p.obs_a.sc + pix);
-                const uchar4 m = ldg4(mk + (int64_t)b * p.mask_a.sb + (int64_t)ch * p.mask_a.sc + pix);
-                v.x = (float)(c_a * ((double)m.x * ((double)m.x * ((double)a.x - (double)o.x))));
-                v.y = (float)(c_a * ((double)m.y * ((double)m.y * ((double)a.y - (double)o.y))));
-                v.z = (float)(c_a * ((double)m.z * ((double)m.z * ((double)a.z - (double)o.z))));
-                v.w = (float)(c_a * ((double)m.w * ((double)m.w * ((double)a.w - (double)o.w))));
+    auto do_a = [&](int item) {
+        const AItem a = a_decode(p, g, item);
+        const int base = p.ylo * p.W + 4 * a.first4;
+        float* pg = g_x0 + ((int64_t)a.b * p.C + a.ch) * plane + base;
+        float* pgd = g_dxdt ? g_dxdt + ((int64_t)a.b * p.C + a.ch) * plane + base : nullptr;
+        if (p.has_a) {
+            const float* pa = x0 + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
+            const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
+            const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
+#pragma unroll 8
+            for (int i = lane; i < a.n4; i += 32) {
+                const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
+                const uchar4 m = ldg4(pm + 4 * i);
+                const double m0 = u8_to_double(m.x), m1 = u8_to_double(m.y), m2 = u8_to_double(m.z), m3 = u8_to_double(m.w);
+                float4 w;
+                w.x = (float)(c_a * (m0 * (m0 * ((double)v.x - (double)o.x))));
+                w.y = (float)(c_a * (m1 * (m1 * ((double)v.y - (double)o.y))));
+                w.z = (float)(c_a * (m2 * (m2 * ((double)v.z - (double)o.z))));
+                w.w = (float)(c_a * (m3 * (m3 * ((double)v.w - (double)o.w))));
+                *reinterpret_cast<float4*>(pg + 4 * i) = w;
             }
-            const int64_t off = ((int64_t)b * p.C + ch) * plane + pix;
-            *reinterpret_cast<float4*>(g_x0 + off) = v;
-            if (g_dxdt) *reinterpret_cast<float4*>(g_dxdt + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pg + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
+        if (pgd)
+            for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pgd + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
 
-    // ---- u-planes
-    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    // ---- u-planes.  Iteration `it` computes the residual of row j = ys - 1 + it (window ua = u[j-1], ub = u[j],
+    //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
+    //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
     const int LW = 1 << g.lw_log2;
-    for (int64_t wi = warp0; wi < g.n_warp_items; wi += nwarps) {
+    RowRing<HAS_D, HAS_O> ring;
+    ring.init(ring_mem, tid);
+    auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
-        const int colc = m.lane_ok ? m.col0 : 0, ch = p.ch_a + m.cu;
-        const float* u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + colc;
-        const float* du = dxp ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + colc : nullptr;
-        const float* ob = p.has_u ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + colc : nullptr;
-        const unsigned char* mk = p.has_u ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + colc : nullptr;
+        ring.bind(p, m, x0, dxp);
+        ring.row0 = m.ys - 2;
+        const int n_it = g.R + 2;
+        // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
+        const int ch = p.ch_a + m.cu, colc = m.lane_ok ? m.col0 : 0;
         float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane + colc;
         float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane + colc : nullptr;
-        const double alpha = __ldg(p.coef + m.b);
-        const double a_s = alpha * p.inv_dx2, kp = -c_p * a_s;
+        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
         const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
-        const int rmax = p.H - 1;
-        auto row = [&](int y) { return (int64_t)min(max(y, 0), rmax) * p.W; };
-
-        // window: ua = u[j-1], ub = u[j], uc = u[j+1]; r2 = r[j-2], r1 = r[j-1]; j starts at ys-1
-        float4 ua = ldg4(u + row(m.ys - 2)), ub = ldg4(u + row(m.ys - 1));
-        float4 n_uc = ldg4(u + row(m.ys));
-        float4 n_dt = du ? ldg4(du + row(m.ys - 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 n_ob = make_float4(0.f, 0.f, 0.f, 0.f);
-        uchar4 n_mk = make_uchar4(0, 0, 0, 0);
-        if (p.has_u) {
-            n_ob = ldg4(ob + row(m.ys - 2));
-            n_mk = ldg4(mk + row(m.ys - 2));
-        }
+        D4v ua = widen(ldg4(ring.u + row_offset(p, m.ys - 2))), ub = widen(ldg4(ring.u + row_offset(p, m.ys - 1)));
         double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-        for (int it = 0; it < g.R + 2; ++it) {
-            const int j = m.ys - 1 + it;                          // residual row computed in this iteration
-            const float4 uc = n_uc, dt = n_dt, o = n_ob;
-            const uchar4 k = n_mk;
-            n_uc = ldg4(u + row(j + 2));                          // prefetch for the next iteration
-            if (du) n_dt = ldg4(du + row(j + 1));
-            if (p.has_u) {
-                n_ob = ldg4(ob + row(j));
-                n_mk = ldg4(mk + row(j));
-            }
-            const int gj = j + p.yg0;
-            float lf = __shfl_up_sync(0xffffffffu, ub.w, 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.x, 1, LW);
-            if (m.left_edge) lf = ub.y;
-            if (m.right_edge) rt = ub.z;
-            const bool rok = m.lane_ok && gj >= 0 && gj < p.Hg && j <= p.yhi;
-            double r0[4];
-            heat_row_residual(gj == 0 ? uc : ua, ub, gj == p.Hg - 1 ? ua : uc, lf, rt, dt, a_s, rok, r0);
+#pragma unroll 3
+        for (int it = 0; it < n_it; ++it) {
+            const int j = m.ys - 1 + it;
+            cp_async_wait<kRing - 3>();                          // elements <= it + 2 have landed
+            const D4v uc = widen(ring.get_u(it + 2));
+            const float4 dt = ring.get_d(it + 1), o = ring.get_o(it);
+            const unsigned k = ring.get_m(it);
+            const int sn = it + kRing;
+            ring.issue(p, sn, sn < n_it + 2, sn < n_it + 1, sn < n_it);
+            double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
+            if (m.left_edge) lf = ub.v[1];
+            if (m.right_edge) rt = ub.v[2];
+            // r of rows outside the grid and of idle lanes is garbage (finite: it is computed from real, clamped
+            // data); it is never consumed: the vertical weights below vanish for out-of-grid neighbours and the
+            // edge lanes zero their horizontal neighbour.
+            double s[4], r0[4];
+            lap_row(ua, ub, uc, lf, rt, s);
+            r0[0] = (double)dt.x - a_s * s[0];
+            r0[1] = (double)dt.y - a_s * s[1];
+            r0[2] = (double)dt.z - a_s * s[2];
+            r0[3] = (double)dt.w - a_s * s[3];
 
-            // output row jo = j - 1: K^T r needs r[jo-1] (r2), r[jo] (r1) with its lane neighbours, r[jo+1] (r0)
             double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1, LW), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1, LW);
             if (m.left_edge) l1 = 0.0;
             if (m.right_edge) q1 = 0.0;
             const int jo = j - 1;
             if (it >= 2 && jo < m.ye && m.out_ok) {
                 const int gjo = jo + p.yg0;
-                const double wu = adj_w(gjo - 1, p.Hg), wd = adj_w(gjo + 1, p.Hg);
+                // transposed-stencil weights of the rows above / below: 2 from a boundary row, 0 from outside
+                const double wu = gjo == 0 ? 0.0 : (gjo == 1 ? 2.0 : 1.0);
+                const double wd = gjo == p.Hg - 1 ? 0.0 : (gjo == p.Hg - 2 ? 2.0 : 1.0);
                 const double a0 = ((wu * r2[0] + wd * r0[0]) + (l1 + r1[1])) - 4.0 * r1[0];
                 const double a1 = ((wu * r2[1] + wd * r0[1]) + (wl1 * r1[0] + r1[2])) - 4.0 * r1[1];
                 const double a2 = ((wu * r2[2] + wd * r0[2]) + (r1[1] + wr2 * r1[3])) - 4.0 * r1[2];
                 const double a3 = ((wu * r2[3] + wd * r0[3]) + (r1[2] + q1)) - 4.0 * r1[3];
                 double v0 = kp * a0, v1 = kp * a1, v2 = kp * a2, v3 = kp * a3;
-                if (p.has_u) {   // ua is u[jo]
-                    v0 += c_u * ((double)k.x * ((double)k.x * ((double)ua.x - (double)o.x)));
-                    v1 += c_u * ((double)k.y * ((double)k.y * ((double)ua.y - (double)o.y)));
-                    v2 += c_u * ((double)k.z * ((double)k.z * ((double)ua.z - (double)o.z)));
-                    v3 += c_u * ((double)k.w * ((double)k.w * ((double)ua.w - (double)o.w)));
+                if (HAS_O) {   // ua is u[jo]
+                    const double m0 = u8_to_double(k & 255u), m1 = u8_to_double((k >> 8) & 255u), m2 = u8_to_double((k >> 16) & 255u), m3 = u8_to_double(k >> 24);
+                    v0 += c_u * (m0 * (m0 * (ua.v[0] - (double)o.x)));
+                    v1 += c_u * (m1 * (m1 * (ua.v[1] - (double)o.y)));
+                    v2 += c_u * (m2 * (m2 * (ua.v[2] - (double)o.z)));
+                    v3 += c_u * (m3 * (m3 * (ua.v[3] - (double)o.w)));
                 }
                 *reinterpret_cast<float4*>(gout + (int64_t)jo * p.W) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
                 if (gdout)
@@ -290,5 +425,7 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
             ua = ub;
             ub = uc;
         }
-    }
+        cp_async_wait<0>();
+    };
+    run_interleaved(warp0, nwarps, g.n_warp_items, g.n_a_items, (tid >> 5) & 1, do_u, do_a);
 }

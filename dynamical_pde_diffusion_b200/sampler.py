@@ -226,21 +226,24 @@ class JointSampler(Sampler):
 
     def _seed_generic(self, engine, xN, dxdt, w, trace_row, want_d, allreduce):
         """Arbitrary ``loss_fn`` plug-in: observation terms from the kernels, the PDE term through the callable
-        (fp64, ``sample.py:345-347``) and torch autograd -- same results, just not fused."""
+        (fp64, ``sample.py:345-347``) and torch autograd.  Everything is summed in fp64 and rounded to the
+        denoiser's fp32 once, like the fused path, so both routes give the same seed."""
         ch_a = self.ch_a
+        x64 = xN.to(F64)
+        d64 = dxdt.to(F64) if dxdt is not None else None
         with torch.enable_grad():
-            xv = xN.to(F64).requires_grad_(True)
-            dv = dxdt.to(F64).requires_grad_(want_d) if dxdt is not None else None
+            xv = x64.detach().requires_grad_(True)
+            dv = d64.detach().requires_grad_(want_d) if d64 is not None else None
             loss_pde = self.loss_fn(xv[:, ch_a:], dv[:, ch_a:] if dv is not None else None, self._run["labels"], **self.loss_kwargs)
             loss_pde = loss_pde.reshape(())
             grads = torch.autograd.grad(w[2] * loss_pde, [xv] + ([dv] if want_d else []), allow_unused=True)
-        g, _ = engine.seed(xN, dxdt, (w[0], w[1], 0.0), trace_row=trace_row, want_dxdt_grad=False, allreduce=allreduce)
+        g, _ = engine.seed(x64, d64, (w[0], w[1], 0.0), trace_row=trace_row, want_dxdt_grad=False, allreduce=allreduce)
         if grads[0] is not None:
-            g = g + grads[0].to(g.dtype)
+            g = g + grads[0]
         trace_row[2] = loss_pde.detach().to(F32)
-        trace_row[3] += (w[2] * loss_pde.detach()).to(F32)
+        trace_row[3] = (engine.scalars[3] + w[2] * loss_pde.detach()).to(F32)
         gd = grads[1].to(F32) if want_d and len(grads) > 1 and grads[1] is not None else None
-        return g, gd
+        return g.to(F32), gd
 
     def finish(self, return_losses=False):
         r = self._run

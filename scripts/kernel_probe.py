@@ -16,12 +16,14 @@ llg = "--llg" in sys.argv
 reps = 3
 dev = torch.device("cuda:0")
 C_, ch_a = (6, 3) if llg else (2, 1)
+if "--uonly" in sys.argv:
+    C_, ch_a = C_ - ch_a, 0
 cu = C_ - ch_a
 s = torch.cuda.current_stream().cuda_stream
 x0 = torch.randn(B, C_, H, W, device=dev)
 dxdt = torch.randn(B, C_, H, W, device=dev)
 mask = torch.rand(H, W, device=dev) < 0.2
-obs_a, obs_u = torch.randn(1, ch_a, H, W, device=dev), torch.randn(1, cu, H, W, device=dev)
+obs_a, obs_u = torch.randn(1, max(ch_a, 1), H, W, device=dev), torch.randn(1, cu, H, W, device=dev)
 w = (20.0, 0.5, 20.0)
 
 
@@ -47,7 +49,7 @@ for name, kind in kinds:
         coef = torch.rand(B, device=dev).double()
     elif kind == PDE_LLG_RESIDUAL:
         coef = (1e4 * torch.randn(B, 3, device=dev)).double()
-    eng = GuidanceEngine(B, C_, ch_a, H, W, kind, dev, obs_a=obs_a, mask_a=mask, obs_u=obs_u, mask_u=mask, sample_coef=coef,
+    eng = GuidanceEngine(B, C_, ch_a, H, W, kind, dev, obs_a=obs_a if ch_a else None, mask_a=mask if ch_a else None, obs_u=obs_u, mask_u=mask, sample_coef=coef,
                          dx=1.0 / (H - 1) if kind == PDE_HEAT else 500e-9 / 64, llg=LLGConstants())
     d = None if kind == PDE_LLG_NORM else dxdt
     nd = 0 if d is None else cu
