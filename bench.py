@@ -229,6 +229,8 @@ def run_ours(args):
     B = args.batch_per_gpu or b_gpu
     net, prob = build_problem(args.workload, B, seed=rank)
     net = net.to(dev)
+    if args.channels_last:                                         # PyTorch-level layout choice for the denoiser only
+        net = net.to(memory_format=torch.channels_last)
     loss_fn, loss_kwargs, provider = pde_plugins(pde, True, prob["dx"])
     smp = dp.JointSampler(net, dev, (H, W), C_, B, ch_a, loss_fn, loss_kwargs, num_steps=n_cfg, out_and_grad_fn=provider)
     z = (prob["zeta_a"], prob["zeta_u"], prob["zeta_pde"])
@@ -281,8 +283,12 @@ def run_ours(args):
     roofline = None
     if dom:
         k = kernels[dom]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")     # ncu dram bytes per launch of this workload
+        if args.workload == "heat128" and B == 64 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": round(k["achieved_gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(k["achieved_gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "note": "bench-workload launch (L2-resident, launch-latency regime); see roofline_large_grid"}
 
     # ---- the same kernels on a grid far larger than L2 (config 5 shape on one GPU) -------------------------
@@ -395,6 +401,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--e2e-budget", type=float, default=45.0, help="seconds the end-to-end sample() call may take")
     ap.add_argument("--ieee", action="store_true", help="IEEE fp32 convolutions instead of the reference's TF32 setting")
+    ap.add_argument("--channels-last", action="store_true", help="run the PyTorch denoiser in NHWC memory format")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-large", action="store_true")
