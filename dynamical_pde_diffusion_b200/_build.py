@@ -12,7 +12,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdpde_b200.so")
-SOURCES = ["update.cu", "guidance.cu"]
+SOURCES = ["update.cu", "guidance.cu", "peer.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

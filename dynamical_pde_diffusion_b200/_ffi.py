@@ -20,7 +20,9 @@ NUM_SCALARS = 8
 EXPORTED = (
     "dpde_abi_version", "dpde_last_error", "dpde_guidance_workspace_bytes", "dpde_guidance_reduce",
     "dpde_guidance_finalize", "dpde_guidance_vjp", "dpde_laplacian", "dpde_sampler_init", "dpde_euler_predict",
-    "dpde_euler_predict_bwd", "dpde_heun_guided_update", "dpde_halo_pack", "dpde_halo_unpack", "dpde_set_fast_path",
+    "dpde_euler_predict_bwd", "dpde_heun_guided_update", "dpde_heun_guided_update_rows", "dpde_halo_pack", "dpde_halo_unpack",
+    "dpde_set_fast_path", "dpde_peer_alloc", "dpde_peer_free", "dpde_peer_export", "dpde_peer_open", "dpde_peer_close",
+    "dpde_halo_push", "dpde_flag_wait",
 )
 
 
@@ -69,6 +71,14 @@ def lib():
     L.dpde_euler_predict.argtypes = [vp, vp, dbl, dbl, vp, i64, vp]
     L.dpde_euler_predict_bwd.argtypes = [vp, dbl, dbl, vp, i64, vp]
     L.dpde_heun_guided_update.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, i64, vp]
+    L.dpde_heun_guided_update_rows.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, i64, i64, i64, i64, vp]
+    L.dpde_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.dpde_peer_free.argtypes = [vp]
+    L.dpde_peer_export.argtypes = [vp, C.c_char_p]
+    L.dpde_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.dpde_peer_close.argtypes = [vp]
+    L.dpde_halo_push.argtypes = [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, vp, vp, C.c_uint64, vp, vp]
+    L.dpde_flag_wait.argtypes = [C.POINTER(vp), i32, C.c_uint64, dbl, vp, vp]
     L.dpde_halo_pack.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.dpde_halo_unpack.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.dpde_set_fast_path.argtypes = [C.c_int]

@@ -146,14 +146,25 @@ __device__ __forceinline__ double heun_point(double x, double x0c, double x0n, d
     return __dsub_rn(x_new, grad);                                                      // sample.py:355
 }
 
-template <bool LAST, bool HAS_GEU, bool HAS_GCUR>
+// ROWS: the update covers elements [first, first + span) of every plane of `plane` elements (owned rows of a row
+// slab); n then counts planes * span.  Flat launches (ROWS == false) index 0..n directly.
+template <bool ROWS>
+__device__ __forceinline__ int64_t elem_index(int64_t i, int64_t span, int64_t plane, int64_t first) {
+    if (!ROWS) return i;
+    const int64_t p = i / span;
+    return p * plane + first + (i - p * span);
+}
+
+template <bool LAST, bool HAS_GEU, bool HAS_GCUR, bool ROWS>
 __global__ void __launch_bounds__(kThreads)
 heun_update_kernel(const double* __restrict__ x, const float* __restrict__ x0c, const float* __restrict__ x0n,
                    const float* __restrict__ geu, const float* __restrict__ gcur, double s_cur, double s_next, double h,
-                   double* __restrict__ o64, float* __restrict__ o32, int64_t n, bool vec) {
+                   double* __restrict__ o64, float* __restrict__ o32, int64_t n, bool vec, int64_t span, int64_t plane,
+                   int64_t first) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = vec ? n / 4 : 0;
-    for (int64_t i = tid; i < n4; i += nth) {
+    for (int64_t q = tid; q < n4; q += nth) {
+        const int64_t i = elem_index<ROWS>(4 * q, span, plane, first) / 4;   // vec implies span, plane, first % 4 == 0
         const D4 xv = load_d4(x + 4 * i);
         const F4 a = load_f4(x0c + 4 * i);
         F4 b{}, ge{}, gc{};
@@ -171,7 +182,8 @@ heun_update_kernel(const double* __restrict__ x, const float* __restrict__ x0c, 
         store_d4(o64 + 4 * i, o);
         store_f4(o32 + 4 * i, f);
     }
-    for (int64_t i = 4 * n4 + tid; i < n; i += nth) {
+    for (int64_t q = 4 * n4 + tid; q < n; q += nth) {
+        const int64_t i = elem_index<ROWS>(q, span, plane, first);
         const double o = heun_point<LAST, HAS_GEU, HAS_GCUR>(
             x[i], (double)x0c[i], LAST ? 0.0 : (double)x0n[i], (!LAST && HAS_GEU) ? (double)geu[i] : 0.0,
             HAS_GCUR ? (double)gcur[i] : 0.0, s_cur, s_next, h);
@@ -230,24 +242,26 @@ int dpde_euler_predict_bwd(const float* g_eu32, double sigma_cur, double sigma_n
     return check_launch("dpde_euler_predict_bwd");
 }
 
-int dpde_heun_guided_update(const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
-                            const float* g_cur, double sigma_cur, double sigma_next, double* x_next64, float* x_next32,
-                            int64_t n, dpde_stream_t stream) {
-    if (!x_cur || !x0_cur || !x_next64 || !x_next32 || n < 0)
-        return fail(DPDE_ERR_INVALID, "dpde_heun_guided_update: null pointer or n < 0");
-    if (!(sigma_cur > 0.0)) return fail(DPDE_ERR_INVALID, "dpde_heun_guided_update: sigma_cur must be > 0");
+namespace {
+int heun_launch(const char* who, const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
+                const float* g_cur, double sigma_cur, double sigma_next, double* x_next64, float* x_next32, int64_t n,
+                bool rows, int64_t span, int64_t plane, int64_t first, dpde_stream_t stream) {
+    if (!x_cur || !x0_cur || !x_next64 || !x_next32 || n < 0) return fail(DPDE_ERR_INVALID, "%s: null pointer or n < 0", who);
+    if (!(sigma_cur > 0.0)) return fail(DPDE_ERR_INVALID, "%s: sigma_cur must be > 0", who);
     const bool last = (x0_next == nullptr);
-    if (!last && !(sigma_next > 0.0))
-        return fail(DPDE_ERR_INVALID, "dpde_heun_guided_update: Heun correction needs sigma_next > 0");
+    if (!last && !(sigma_next > 0.0)) return fail(DPDE_ERR_INVALID, "%s: Heun correction needs sigma_next > 0", who);
     if (n == 0) return DPDE_OK;
-    const bool vec = aligned16(x_cur) && aligned16(x0_cur) && aligned16(x_next64) && aligned16(x_next32) &&
-                     (last || aligned16(x0_next)) && (!g_eu || aligned16(g_eu)) && (!g_cur || aligned16(g_cur));
+    bool vec = aligned16(x_cur) && aligned16(x0_cur) && aligned16(x_next64) && aligned16(x_next32) &&
+               (last || aligned16(x0_next)) && (!g_eu || aligned16(g_eu)) && (!g_cur || aligned16(g_cur));
+    if (rows) vec = vec && span % 4 == 0 && plane % 4 == 0 && first % 4 == 0;
     const double h = sigma_next - sigma_cur;
     const int grid = stream_grid(n);
     cudaStream_t s = (cudaStream_t)stream;
-#define DPDE_LAUNCH(L, GE, GC)                                                                                     \
-    heun_update_kernel<L, GE, GC><<<grid, kThreads, 0, s>>>(x_cur, x0_cur, x0_next, g_eu, g_cur, sigma_cur, sigma_next, \
-                                                            h, x_next64, x_next32, n, vec)
+#define DPDE_LAUNCH2(L, GE, GC, R)                                                                                    \
+    heun_update_kernel<L, GE, GC, R><<<grid, kThreads, 0, s>>>(x_cur, x0_cur, x0_next, g_eu, g_cur, sigma_cur, sigma_next, \
+                                                               h, x_next64, x_next32, n, vec, span, plane, first)
+#define DPDE_LAUNCH(L, GE, GC) \
+    do { if (rows) DPDE_LAUNCH2(L, GE, GC, true); else DPDE_LAUNCH2(L, GE, GC, false); } while (0)
     if (last) {
         if (g_cur) DPDE_LAUNCH(true, false, true); else DPDE_LAUNCH(true, false, false);
     } else if (g_eu) {
@@ -256,7 +270,26 @@ int dpde_heun_guided_update(const double* x_cur, const float* x0_cur, const floa
         if (g_cur) DPDE_LAUNCH(false, false, true); else DPDE_LAUNCH(false, false, false);
     }
 #undef DPDE_LAUNCH
-    return check_launch("dpde_heun_guided_update");
+#undef DPDE_LAUNCH2
+    return check_launch(who);
+}
+}  // namespace
+
+int dpde_heun_guided_update(const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
+                            const float* g_cur, double sigma_cur, double sigma_next, double* x_next64, float* x_next32,
+                            int64_t n, dpde_stream_t stream) {
+    return heun_launch("dpde_heun_guided_update", x_cur, x0_cur, x0_next, g_eu, g_cur, sigma_cur, sigma_next, x_next64,
+                       x_next32, n, false, n, n, 0, stream);
+}
+
+int dpde_heun_guided_update_rows(const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
+                                 const float* g_cur, double sigma_cur, double sigma_next, double* x_next64,
+                                 float* x_next32, int64_t planes, int64_t plane_elems, int64_t first, int64_t count,
+                                 dpde_stream_t stream) {
+    if (planes < 0 || plane_elems < 0 || first < 0 || count < 0 || first + count > plane_elems)
+        return fail(DPDE_ERR_INVALID, "dpde_heun_guided_update_rows: need 0 <= first, first + count <= plane_elems");
+    return heun_launch("dpde_heun_guided_update_rows", x_cur, x0_cur, x0_next, g_eu, g_cur, sigma_cur, sigma_next,
+                       x_next64, x_next32, planes * count, true, count, plane_elems, first, stream);
 }
 
 }  // extern "C"

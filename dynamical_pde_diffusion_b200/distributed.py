@@ -57,6 +57,14 @@ def full_latents(batch, channels, shape, seed, device="cpu"):
     return torch.randn((batch, channels, *shape), generator=g, dtype=torch.float64, device=device)
 
 
+def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """(world, *t.shape) stack of every rank's ``t`` (concatenated-output form: accepted by NCCL and gloo alike)."""
+    t = t.contiguous()
+    out = torch.empty((world * t.shape[0], *t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.view(world, *t.shape)
+
+
 def gather_samples(x_local: torch.Tensor, trace_local, batch: int, group=None, device=None):
     """All-gather per-rank samples (B_r,C,H,W) and loss traces (N,4) -> ((B,C,H,W) tensor, (G,N,4) array) on every rank.
 
@@ -71,15 +79,12 @@ def gather_samples(x_local: torch.Tensor, trace_local, batch: int, group=None, d
     pad = max(sizes)
     buf = torch.zeros((pad, *x_local.shape[1:]), dtype=x_local.dtype, device=dev)
     buf[: sizes[rank]] = x_local.to(dev)
-    out = torch.empty((world, *buf.shape), dtype=buf.dtype, device=dev)
-    dist.all_gather_into_tensor(out, buf, group=group)
+    out = _all_gather(buf, world, group)
     x = torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
     traces = None
     if trace_local is not None:
         t = torch.as_tensor(trace_local, dtype=torch.float32).to(dev).contiguous()
-        tout = torch.empty((world, *t.shape), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(tout, t, group=group)
-        traces = tout.cpu().numpy()
+        traces = _all_gather(t, world, group).cpu().numpy()
     return x.to(x_local.device), traces
 
 

@@ -187,6 +187,12 @@ class JointSampler(Sampler):
 
     def step(self):
         """One guided Heun step (``sample.py:320-357``); advances the internal state, no host sync."""
+        ctx = self._step_front()
+        self._step_back(ctx)
+
+    def _step_front(self):
+        """Denoiser evaluation(s), Euler predictor and pass 1 (the three sums).  With a cross-rank all-reduce
+        (``coupled`` batch shards, row slabs) the sums are left un-finalised for the caller to reduce."""
         r = self._run
         i, N, B = r["i"], r["N"], r["B"]
         s_cur, s_next = r["sigmas"][i], r["sigmas"][i + 1]
@@ -208,21 +214,44 @@ class JointSampler(Sampler):
         w = (za, zu, zp) if i <= 0.8 * N else (0.1 * za, 0.1 * zu, zp)
         dx_c = _f32c(dxdt.detach()) if dxdt is not None else None
         want_d = dxdt is not None and dxdt.requires_grad
+        ctx = dict(x32=x32, stash=stash, x0_1c=x0_1c, xN=xN, dxdt=dxdt, dx_c=dx_c, want_d=want_d, w=w, last=last,
+                   s_cur=s_cur, s_next=s_next)
         if r["fused"]:
-            g, gd = engine.seed(xN.detach(), dx_c, w, trace_row=r["trace"][i], want_dxdt_grad=want_d, allreduce=r["allreduce"])
+            engine.reduce(xN.detach(), dx_c, w, trace_row=r["trace"][i] if r["allreduce"] is None else None,
+                          finalize=r["allreduce"] is None)
+        return ctx
+
+    def _step_back(self, ctx):
+        """(all-reduce of the sums,) seed gradient, backward through the denoiser(s), fused Heun + guidance update."""
+        r = self._run
+        i, engine = r["i"], r["engine"]
+        xN, dxdt, dx_c, want_d, w, last = ctx["xN"], ctx["dxdt"], ctx["dx_c"], ctx["want_d"], ctx["w"], ctx["last"]
+        if r["fused"]:
+            if r["allreduce"] is not None:
+                r["allreduce"](engine.sums)
+                engine.finalize(r["trace"][i])
+            g, gd = engine.vjp(xN.detach(), dx_c, w, want_d)
         else:
             g, gd = self._seed_generic(engine, xN.detach(), dx_c, w, r["trace"][i], want_d, r["allreduce"])
         outs, seeds = [xN], [g]
         if want_d and gd is not None:
             outs.append(dxdt)
             seeds.append(gd.to(dxdt.dtype))
-        (g_cur,) = torch.autograd.grad(outs, [x32], grad_outputs=seeds, allow_unused=True)
-        g_eu = stash.get("g_eu")
-        x64n, x32n = r["x64_alt"], torch.empty_like(r["x32"])
-        _ffi.call("dpde_heun_guided_update", r["x64"].data_ptr(), x0_1c.data_ptr(), None if last else xN.data_ptr(),
-                  g_eu.data_ptr() if g_eu is not None else None, _f32c(g_cur).data_ptr() if g_cur is not None else None,
-                  s_cur, s_next, x64n.data_ptr(), x32n.data_ptr(), x64n.numel(), _stream())
+        (g_cur,) = torch.autograd.grad(outs, [ctx["x32"]], grad_outputs=seeds, allow_unused=True)
+        g_eu = ctx["stash"].get("g_eu")
+        x64n = r["x64_alt"]
+        x32n = r["x32_alt"] if r.get("x32_alt") is not None else torch.empty_like(r["x32"])
+        self._launch_update(r["x64"], ctx["x0_1c"], None if last else xN, g_eu, _f32c(g_cur) if g_cur is not None else None,
+                            ctx["s_cur"], ctx["s_next"], x64n, x32n)
+        x32_old = r["x32"].detach().requires_grad_(False) if r.get("x32_alt") is not None else None
         r["x64"], r["x64_alt"], r["x32"], r["i"] = x64n, r["x64"], x32n, i + 1
+        if x32_old is not None:
+            r["x32_alt"] = x32_old
+
+    def _launch_update(self, x64, x0_1c, x0_2, g_eu, g_cur, s_cur, s_next, x64n, x32n):
+        _ffi.call("dpde_heun_guided_update", x64.data_ptr(), x0_1c.data_ptr(), x0_2.data_ptr() if x0_2 is not None else None,
+                  g_eu.data_ptr() if g_eu is not None else None, g_cur.data_ptr() if g_cur is not None else None,
+                  s_cur, s_next, x64n.data_ptr(), x32n.data_ptr(), x64n.numel(), _stream())
 
     def _seed_generic(self, engine, xN, dxdt, w, trace_row, want_d, allreduce):
         """Arbitrary ``loss_fn`` plug-in: observation terms from the kernels, the PDE term through the callable

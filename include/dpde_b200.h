@@ -133,6 +133,42 @@ int dpde_heun_guided_update(const double* x_cur, const float* x0_cur, const floa
                             const float* g_cur, double sigma_cur, double sigma_next, double* x_next64, float* x_next32,
                             int64_t n, dpde_stream_t stream);
 
+/* Same update restricted to elements [first, first + count) of each of `planes` planes of plane_elems elements --
+   the owned rows of a row slab, so ghost rows (which the neighbours push, dpde_halo_push) are never written. */
+int dpde_heun_guided_update_rows(const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
+                                 const float* g_cur, double sigma_cur, double sigma_next, double* x_next64,
+                                 float* x_next32, int64_t planes, int64_t plane_elems, int64_t first, int64_t count,
+                                 dpde_stream_t stream);
+
+/* ---- Peer memory: row-slab halo exchange over NVLink (one process per GPU; nothing like it in the reference) ----
+   dpde_peer_alloc returns zero-filled device memory that can be exported to the other ranks of the box
+   (cudaIpc); dpde_peer_export / dpde_peer_open move the 64-byte handle / map a neighbour's allocation into this
+   process (peer access over NVLink is enabled by the mapping).  The caller keeps allocations alive until every
+   rank has closed its mappings. */
+#define DPDE_IPC_HANDLE_BYTES 64
+int dpde_peer_alloc(size_t bytes, void** ptr);
+int dpde_peer_free(void* ptr);
+int dpde_peer_export(const void* ptr, unsigned char handle[DPDE_IPC_HANDLE_BYTES]);
+int dpde_peer_open(const unsigned char handle[DPDE_IPC_HANDLE_BYTES], void** ptr);
+int dpde_peer_close(void* ptr);
+
+/* Halo push: copy this rank's owned boundary rows of `field` (planes x H_local x W, ghost rows included) straight
+   into the neighbours' ghost rows through their mapped buffers --
+     rows [halo, 2 halo)                   -> dst_up   rows [H_up - halo, H_up)      (dst_up: H_up rows per plane)
+     rows [H_local - 2 halo, H_local - halo) -> dst_down rows [0, halo)              (dst_down: H_down rows per plane)
+   then, after a system-scope fence, store `value` into *flag_up / *flag_down (8-byte words in the neighbours'
+   memory) with release semantics.  NULL destination = no neighbour on that side.  `ticket` is a zeroed 4-byte
+   word in LOCAL device memory (left zeroed). */
+int dpde_halo_push(const void* field, int32_t dtype, int64_t planes, int32_t H_local, int32_t W, int32_t halo,
+                   void* dst_up, int32_t H_up, void* dst_down, int32_t H_down, void* flag_up, void* flag_down,
+                   uint64_t value, void* ticket, dpde_stream_t stream);
+
+/* Block the stream until every one of the n (<= 4) LOCAL 8-byte flags is >= value (acquire, system scope), i.e. the
+   neighbours' pushes have landed.  After timeout_s seconds it gives up and writes 1 to *status (device int32,
+   otherwise untouched) -- a stuck neighbour must not hang the GPU. */
+int dpde_flag_wait(const void* const* flags, int32_t n, uint64_t value, double timeout_s, int32_t* status,
+                   dpde_stream_t stream);
+
 /* Row-slab halo staging for `planes` local images of H_local rows (ghost rows included), W columns.
    pack:   owned rows [halo, 2 halo) -> send_up, owned rows [H_local - 2 halo, H_local - halo) -> send_down
    unpack: recv_up -> ghost rows [0, halo),      recv_down -> ghost rows [H_local - halo, H_local)
