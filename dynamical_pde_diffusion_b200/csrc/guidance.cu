@@ -35,6 +35,7 @@ struct Params {
     int B, C, ch_a, H, W, kind, has_a, has_u;
     int Hg, yg0, ylo, yhi;  // row slab: global height, global row of local row 0, owned local rows [ylo, yhi)
     int n_u_units, units_per_sample;
+    int obs_l1;             // marching kernels: fetch observation rows with L1 allocation
     int tile_w, tile_h, tw_log2, tiles_x, tiles_y;
     int64_t tiles_per_plane, n_tiles;
     View x0, dxdt, obs_a, mask_a, obs_u, mask_u;
@@ -566,11 +567,16 @@ laplacian_kernel(const T* __restrict__ u, T* __restrict__ out, int64_t planes, i
 }
 
 #include "heat_march.cuh"
+#include "llg_tile.cuh"
 
 // =========================================================================================================
 // host side
 // =========================================================================================================
 bool g_fast_path = true;
+// experiment knobs (dpde_set_tuning): [0] strip layout 0 = 120 columns + 1 halo lane, 1 = 112 + 2 (sector aligned);
+// [1] unused; [2] rows per chunk (0 = automatic); [3] 1 = never pair a-planes in the reduce pass; [4] 1 = pair them in
+// the VJP pass too; [5] 1 = observation rows through L1 (cp.async.ca)
+int g_tuning[8] = {1, 0, 0, 0, 0, 0, 0, 0};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
@@ -578,7 +584,7 @@ inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
 // Can the row-marching kernels take this problem?  (else the generic tile kernels run)
 bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
     if (!g_fast_path || p.kind != DPDE_PDE_HEAT || p.x0.dtype != DPDE_F32 || p.W % 4 != 0) return false;
-    if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * ((p.H + 7) / 8) * ((p.W + 119) / 120) >= (1ll << 30)) return false;
+    if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * ((p.H + 7) / 8) * ((p.W + 111) / 112) >= (1ll << 30)) return false;
     if (!al(p.x0.p, 16) || !s4(p.x0)) return false;
     if (p.dxdt.p && (!al(p.dxdt.p, 16) || !s4(p.dxdt))) return false;
     if (g_x0 && !al(g_x0, 16)) return false;
@@ -598,13 +604,16 @@ MarchGeom march_geometry(const Params& p) {
         while (lw * 4 < p.W) { lw <<= 1; ++l2; }
         g.lw_log2 = l2; g.segs_per_warp = 32 / lw; g.strips = 1; g.strip_w = p.W; g.halo_lane = 0;
     } else {
-        g.lw_log2 = 5; g.segs_per_warp = 1; g.strip_w = 120; g.strips = (p.W + 119) / 120; g.halo_lane = 1;
+        g.lw_log2 = 5; g.segs_per_warp = 1;
+        if (g_tuning[0] == 0) { g.strip_w = 120; g.halo_lane = 1; } else { g.strip_w = 112; g.halo_lane = 2; }
+        g.strips = (p.W + g.strip_w - 1) / g.strip_w;
     }
     // rows per chunk: long chunks amortise the 2-row warm-up, short ones expose more warps on small problems
     const int64_t per_row_items = (int64_t)g.strips * p.n_u_units * p.B;
     const int64_t want_warps = (int64_t)sm_count() * 16;
     int R = 32;
     while (R > 8 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
+    if (g_tuning[2] > 0) R = g_tuning[2];
     g.R = R;
     g.chunks = (rows + R - 1) / R;
     g.n_seg_items = (int)((int64_t)g.chunks * per_row_items);
@@ -615,41 +624,172 @@ MarchGeom march_geometry(const Params& p) {
     return g;
 }
 
+// 0: a-planes are separate streaming items; 1: paired with the u-plane of the same index; 2: paired, mask_a empty
+inline int pairing(const Params& p, bool vjp) {
+    return ((vjp ? g_tuning[4] != 0 : g_tuning[3] == 0) && p.ch_a >= 1 && p.ch_a == p.n_u_units) ? (p.has_a ? 1 : 2) : 0;
+}
+
 template <typename K>
-int march_grid(K kernel, const MarchGeom& g) {
+int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
     // opt in to > 48 KB dynamic shared memory once per kernel instantiation, then size a persistent grid
-    static thread_local const void* configured[16] = {nullptr};
+    static thread_local const void* configured[64] = {nullptr};
     bool seen = false;
     for (const void* k : configured) seen = seen || k == (const void*)kernel;
     if (!seen) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         for (auto& k : configured)
             if (!k) { k = (const void*)kernel; break; }
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, kRingBytes) != cudaSuccess || occ < 1) occ = 1;
-    int64_t need = ((int64_t)g.n_warp_items + g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    int64_t need = ((int64_t)g.n_warp_items + (paired ? 0 : g.n_a_items) + kThreads / 32 - 1) / (kThreads / 32);
     int64_t grid = (int64_t)sm_count() * occ;
     if (grid > need) grid = need;
     if (grid > kMaxPartials) grid = kMaxPartials;
     return (int)(grid < 1 ? 1 : grid);
 }
 
+template <bool HAS_D, bool HAS_O, int PA>
+int launch_march_reduce_pa(const Params& p, const MarchGeom& g, double* partials, unsigned int* ticket, double* sums, int finalize,
+                           double* scal, float* trace, cudaStream_t s) {
+    constexpr int smem = ring_bytes(PA);
+    auto k = heat_march_reduce_kernel<HAS_D, HAS_O, PA>;
+    k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    return check_launch("dpde_guidance_reduce (march)");
+}
+
 template <bool HAS_D, bool HAS_O>
 int launch_march_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal,
                         float* trace, cudaStream_t s) {
     const MarchGeom g = march_geometry(p);
-    auto k = heat_march_reduce_kernel<HAS_D, HAS_O>;
-    k<<<march_grid(k, g), kThreads, kRingBytes, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
-    return check_launch("dpde_guidance_reduce (march)");
+    switch (pairing(p, false)) {
+        case 1: return launch_march_reduce_pa<HAS_D, HAS_O, 1>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        case 2: return launch_march_reduce_pa<HAS_D, HAS_O, 2>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        default: return launch_march_reduce_pa<HAS_D, HAS_O, 0>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+    }
+}
+
+template <bool HAS_D, bool HAS_O, int PA>
+int launch_march_vjp_pa(const Params& p, const MarchGeom& g, const double* scal, const double* upstream, float* g_x0,
+                        float* g_dxdt, cudaStream_t s) {
+    constexpr int smem = ring_bytes(PA);
+    auto k = heat_march_vjp_kernel<HAS_D, HAS_O, PA>;
+    k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    return check_launch("dpde_guidance_vjp (march)");
 }
 
 template <bool HAS_D, bool HAS_O>
 int launch_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
     const MarchGeom g = march_geometry(p);
-    auto k = heat_march_vjp_kernel<HAS_D, HAS_O>;
-    k<<<march_grid(k, g), kThreads, kRingBytes, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
-    return check_launch("dpde_guidance_vjp (march)");
+    switch (pairing(p, true)) {
+        case 1: return launch_march_vjp_pa<HAS_D, HAS_O, 1>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        case 2: return launch_march_vjp_pa<HAS_D, HAS_O, 2>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        default: return launch_march_vjp_pa<HAS_D, HAS_O, 0>(p, g, scal, upstream, g_x0, g_dxdt, s);
+    }
+}
+
+// ---- LLG fast path (llg_tile.cuh) ----------------------------------------------------------------------
+bool llg_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
+    if (!g_fast_path || (p.kind != DPDE_PDE_LLG_RESIDUAL && p.kind != DPDE_PDE_LLG_NORM)) return false;
+    if (p.x0.dtype != DPDE_F32 || p.W % 4 != 0 || p.W < 4) return false;
+    if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * (((int64_t)p.H * p.W + 1023) / 1024 + p.H + p.W) >= (1ll << 30)) return false;
+    if (!al(p.x0.p, 16) || !s4(p.x0)) return false;
+    if (p.dxdt.p && (!al(p.dxdt.p, 16) || !s4(p.dxdt))) return false;
+    if (g_x0 && !al(g_x0, 16)) return false;
+    if (g_dxdt && !al(g_dxdt, 16)) return false;
+    if (p.has_a && (p.obs_a.dtype != DPDE_F32 || p.mask_a.dtype != DPDE_U8 || !al(p.obs_a.p, 16) || !al(p.mask_a.p, 4) ||
+                    !s4(p.obs_a) || !s4(p.mask_a))) return false;
+    if (p.has_u && (p.obs_u.dtype != DPDE_F32 || p.mask_u.dtype != DPDE_U8 || !al(p.obs_u.p, 16) || !al(p.mask_u.p, 4) ||
+                    !s4(p.obs_u) || !s4(p.mask_u))) return false;
+    return true;
+}
+
+struct LlgGeom {
+    MarchGeom g;  // only the a-plane fields are used
+    int tw, tiles_x, n_tiles, n_norm_items;
+};
+
+LlgGeom llg_geometry(const Params& p) {
+    LlgGeom L{};
+    const int rows = p.yhi - p.ylo;
+    L.tw = p.W >= 64 ? 64 : p.W >= 32 ? 32 : 16;
+    const int th = 1024 / L.tw;
+    L.tiles_x = (p.W + L.tw - 1) / L.tw;
+    L.n_tiles = p.B * ((rows + th - 1) / th) * L.tiles_x;
+    L.g.a_plane4 = (int)((int64_t)rows * p.W / 4);
+    L.g.a_blocks_per_plane = (L.g.a_plane4 + kABlock - 1) / kABlock;
+    L.g.n_a_items = L.g.a_blocks_per_plane * p.ch_a * p.B;
+    L.n_norm_items = L.g.a_blocks_per_plane * p.B;
+    return L;
+}
+
+template <typename K>
+int llg_grid(K kernel, int smem, int64_t cta_items) {
+    static thread_local const void* configured[16] = {nullptr};
+    bool seen = false;
+    for (const void* k : configured) seen = seen || k == (const void*)kernel;
+    if (!seen) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (auto& k : configured)
+            if (!k) { k = (const void*)kernel; break; }
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    int64_t grid = (int64_t)sm_count() * occ;
+    if (grid > cta_items) grid = cta_items;
+    if (grid > kMaxPartials) grid = kMaxPartials;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+template <int TW>
+int launch_llg_tile_reduce(const Params& p, const LlgGeom& L, double* partials, unsigned int* ticket, double* sums, int finalize,
+                           double* scal, float* trace, cudaStream_t s) {
+    constexpr int smem = LlgTile<TW>::smem_bytes(false);
+    auto k = llg_tile_reduce_kernel<TW>;
+    const int64_t items = (int64_t)L.n_tiles + (L.g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
+    k<<<llg_grid(k, smem, items), kThreads, smem, s>>>(p, L.g, L.tiles_x, L.n_tiles, partials, ticket, sums, finalize, scal, trace);
+    return check_launch("dpde_guidance_reduce (llg tile)");
+}
+
+template <int TW>
+int launch_llg_tile_vjp(const Params& p, const LlgGeom& L, const double* scal, const double* upstream, float* g_x0, float* g_dxdt,
+                        cudaStream_t s) {
+    constexpr int smem = LlgTile<TW>::smem_bytes(true);
+    auto k = llg_tile_vjp_kernel<TW>;
+    const int64_t items = (int64_t)L.n_tiles + (L.g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
+    k<<<llg_grid(k, smem, items), kThreads, smem, s>>>(p, L.g, L.tiles_x, L.n_tiles, scal, upstream, g_x0, g_dxdt);
+    return check_launch("dpde_guidance_vjp (llg tile)");
+}
+
+int launch_llg_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal,
+                      float* trace, cudaStream_t s) {
+    const LlgGeom L = llg_geometry(p);
+    if (p.kind == DPDE_PDE_LLG_NORM) {
+        auto k = llg_norm_reduce_kernel;
+        const int64_t items = ((int64_t)L.n_norm_items + L.g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
+        k<<<llg_grid(k, 0, items), kThreads, 0, s>>>(p, L.g, L.n_norm_items, partials, ticket, sums, finalize, scal, trace);
+        return check_launch("dpde_guidance_reduce (llg norm)");
+    }
+    switch (L.tw) {
+        case 64: return launch_llg_tile_reduce<64>(p, L, partials, ticket, sums, finalize, scal, trace, s);
+        case 32: return launch_llg_tile_reduce<32>(p, L, partials, ticket, sums, finalize, scal, trace, s);
+        default: return launch_llg_tile_reduce<16>(p, L, partials, ticket, sums, finalize, scal, trace, s);
+    }
+}
+
+int launch_llg_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
+    const LlgGeom L = llg_geometry(p);
+    if (p.kind == DPDE_PDE_LLG_NORM) {
+        auto k = llg_norm_vjp_kernel;
+        const int64_t items = ((int64_t)L.n_norm_items + L.g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
+        k<<<llg_grid(k, 0, items), kThreads, 0, s>>>(p, L.g, L.n_norm_items, scal, upstream, g_x0, g_dxdt);
+        return check_launch("dpde_guidance_vjp (llg norm)");
+    }
+    switch (L.tw) {
+        case 64: return launch_llg_tile_vjp<64>(p, L, scal, upstream, g_x0, g_dxdt, s);
+        case 32: return launch_llg_tile_vjp<32>(p, L, scal, upstream, g_x0, g_dxdt, s);
+        default: return launch_llg_tile_vjp<16>(p, L, scal, upstream, g_x0, g_dxdt, s);
+    }
 }
 
 View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }
@@ -695,6 +835,7 @@ int validate_and_fill(const dpde_guidance_desc* d, int tile_pix, Params& p, cons
     p.has_a = d->has_a != 0; p.has_u = d->has_u != 0;
     const bool llg = d->pde_kind == DPDE_PDE_LLG_NORM || d->pde_kind == DPDE_PDE_LLG_RESIDUAL;
     p.n_u_units = llg ? 1 : cu;
+    p.obs_l1 = g_tuning[5];
     p.units_per_sample = d->ch_a + p.n_u_units;
     p.tile_w = d->W > 64 ? 128 : d->W > 32 ? 64 : d->W > 16 ? 32 : 16;
     p.tile_h = tile_pix / p.tile_w;
@@ -776,6 +917,12 @@ int dpde_set_fast_path(int enable) {
     return old;
 }
 
+int dpde_set_tuning(int key, int value) {
+    if (key < 0 || key >= 8) return fail(DPDE_ERR_INVALID, "dpde_set_tuning: key must be in [0, 8)");
+    g_tuning[key] = value;
+    return DPDE_OK;
+}
+
 size_t dpde_guidance_workspace_bytes(void) { return (size_t)(3 * kMaxPartials + 2) * sizeof(double); }
 
 int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize, double* scalars,
@@ -794,6 +941,7 @@ int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double
                  : (o ? launch_march_reduce<false, true>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
                       : launch_march_reduce<false, false>(p, partials, ticket, sums, finalize, scalars, trace_row, s));
     }
+    if (llg_eligible(p, nullptr, nullptr)) return launch_llg_reduce(p, partials, ticket, sums, finalize, scalars, trace_row, s);
     return p.x0.dtype == DPDE_F32 ? launch_reduce<float>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
                                   : launch_reduce<double>(p, partials, ticket, sums, finalize, scalars, trace_row, s);
 }
@@ -819,6 +967,7 @@ int dpde_guidance_vjp(const dpde_guidance_desc* desc, const double* scalars, con
         return d ? (o ? launch_march_vjp<true, true>(p, scalars, upstream, gx, gd, s) : launch_march_vjp<true, false>(p, scalars, upstream, gx, gd, s))
                  : (o ? launch_march_vjp<false, true>(p, scalars, upstream, gx, gd, s) : launch_march_vjp<false, false>(p, scalars, upstream, gx, gd, s));
     }
+    if (llg_eligible(p, g_x0, g_dxdt)) return launch_llg_vjp(p, scalars, upstream, (float*)g_x0, (float*)g_dxdt, s);
     return p.x0.dtype == DPDE_F32 ? launch_vjp<float>(p, scalars, upstream, g_x0, g_dxdt, s)
                                   : launch_vjp<double>(p, scalars, upstream, g_x0, g_dxdt, s);
 }

@@ -18,8 +18,10 @@
 //     their results multiplied by zero;
 //   * the three-row windows are kept in fp64, so every loaded value is converted once (F2F.F64.F32 issues at a
 //     quarter of the DFMA rate) and the uint8 mask is widened with the 2^52 trick (one DADD, no I2F);
-//   * grids wider than 128 columns are cut into strips of 120 output columns + one halo lane on each side
-//     (halo reads hit L2); narrow grids pack several row segments into one warp (W = 64: two, W = 16: eight).
+//   * grids wider than 128 columns are cut into strips of 112 output columns + two halo lanes on each side, so that
+//     every warp access starts on a 32-byte sector boundary (one halo lane would do for the stencil, but a strip
+//     starting at column 120 k - 4 splits every 128-byte wavefront over two lines: +25 % sectors on the L2
+//     crossbar, measured); narrow grids pack several row segments into one warp (W = 64: two, W = 16: eight).
 // A lane spends ~30 instructions per pixel; arithmetic and accumulation stay fp64 (see guidance.cu header).
 //
 // Eligibility (checked on the host, else the generic tile kernel runs): fp32 fields, W % 4 == 0, 16-byte aligned
@@ -37,13 +39,22 @@ constexpr int kABlock = 1024;            // float4 per a-plane work item (4096 p
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uchar4 ldg4(const unsigned char* p) { return __ldg(reinterpret_cast<const uchar4*>(p)); }
 
-constexpr int kRing = 8;                                            // ring elements (rows) per lane, power of two
-constexpr int kRingBytes = kRing * kThreads * (3 * 16 + 4);         // dynamic shared memory per CTA (106496 B)
+// Ring depth (rows per lane, power of two) and dynamic shared memory per CTA.  PA = 0: a-planes are separate
+// streaming work items (8-deep ring of u / dudt / obs_u / mask_u: 106496 B);  PA = 1 / 2: every marching item also
+// carries the a-plane of the same index (requires ch_a == number of u-planes), whose row, observation and mask
+// (PA == 1; PA == 2: mask_a empty, nothing to read, ring as PA = 0) ride in the same ring element -- 4 deep, 90112 B.
+__host__ __device__ constexpr int ring_depth(int PA) { return PA == 1 ? 4 : 8; }
+__host__ __device__ constexpr int ring_bytes(int PA) { return ring_depth(PA) * kThreads * (PA == 1 ? 5 * 16 + 2 * 4 : 3 * 16 + 4); }
 
 // shared-memory operands are 32-bit shared-window addresses computed once per thread (the generic->shared
 // conversion otherwise costs ~6 instructions per copy)
 __device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+// .ca: allocate in L1.  Observation / mask rows are broadcast over the batch and the warps of a CTA work on
+// consecutive samples of the same tile, so all but the first reader hit in L1 and never cross the L2 crossbar.
+__device__ __forceinline__ void cp_async16_ca(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async4(unsigned smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
@@ -106,48 +117,75 @@ __device__ __forceinline__ int row_offset(const Params& p, int y) {
     return min(max(gy - p.yg0, 0), p.H - 1) * p.W;
 }
 
-// Per-lane prefetch ring.  Element s holds u, dudt, obs and mask of row (row0 + s) for the lane's four columns.
-// HAS_D / HAS_O: dudt / observation operands present (compile-time, so the loop carries no pointer tests).
-template <bool HAS_D, bool HAS_O>
+// Per-lane prefetch ring.  Element s holds u, dudt, obs and mask (and, paired, a / obs_a / mask_a) of row (row0 + s)
+// for the lane's four columns.  HAS_D / HAS_O / PA are compile-time, so the loop carries no pointer tests.
+template <bool HAS_D, bool HAS_O, int PA>
 struct RowRing {
-    unsigned su, sd, so, sm;                 // shared-window byte addresses of this lane's slot 0 in each field ring
-    const float *u, *du, *ob;
-    const unsigned char* mk;
+    static constexpr int RD = ring_depth(PA);
+    unsigned su, sd, so, sm, sa, soa, sma;   // shared-window byte addresses of this lane's slot 0 in each field ring
+    const float *u, *du, *ob, *a, *oa;
+    const unsigned char *mk, *ma;
     int row0;
+    bool OBS_L1;                             // observation rows through L1 (they broadcast over the batch)
 
-    static __device__ __forceinline__ unsigned slot16(int s) { return (unsigned)(s & (kRing - 1)) * (kThreads * 16); }
-    static __device__ __forceinline__ unsigned slot4(int s) { return (unsigned)(s & (kRing - 1)) * (kThreads * 4); }
+    static __device__ __forceinline__ unsigned slot16(int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); }
+    static __device__ __forceinline__ unsigned slot4(int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); }
 
-    // start the copies of element s (fields selected by warp-uniform flags); always commits exactly one group
+    // start the copies of element s (fields selected by warp-uniform flags); always commits exactly one group.
+    // fo also selects the a-plane fields: they are consumed together with the observation of the same row.
+    int colc;                                // the lane's first column (clamped to 0 for idle lanes)
     __device__ __forceinline__ void issue(const Params& p, int s, bool fu, bool fd, bool fo) const {
         const int off = row_offset(p, row0 + s);
-        if (fu) cp_async16(su + slot16(s), u + off);
-        if (HAS_D && fd) cp_async16(sd + slot16(s), du + off);
+        if (fu) cp_async16(su + slot16(s), (u + off) + colc);
+        if (HAS_D && fd) cp_async16(sd + slot16(s), (du + off) + colc);
         if (HAS_O && fo) {
-            cp_async16(so + slot16(s), ob + off);
-            cp_async4(sm + slot4(s), mk + off);
+            if (OBS_L1) cp_async16_ca(so + slot16(s), (ob + off) + colc);
+            else cp_async16(so + slot16(s), (ob + off) + colc);
+            cp_async4(sm + slot4(s), (mk + off) + colc);
+        }
+        if (PA == 1 && fo) {
+            cp_async16(sa + slot16(s), (a + off) + colc);
+            if (OBS_L1) cp_async16_ca(soa + slot16(s), (oa + off) + colc);
+            else cp_async16(soa + slot16(s), (oa + off) + colc);
+            cp_async4(sma + slot4(s), (ma + off) + colc);
         }
         cp_async_commit();
     }
+    __device__ __forceinline__ float4 direct_u(const Params& p, int y) const { return ldg4((u + row_offset(p, y)) + colc); }
     __device__ __forceinline__ float4 get_u(int s) const { return lds128(su + slot16(s)); }
     __device__ __forceinline__ float4 get_d(int s) const { return HAS_D ? lds128(sd + slot16(s)) : make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ float4 get_o(int s) const { return HAS_O ? lds128(so + slot16(s)) : make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ unsigned get_m(int s) const { return HAS_O ? lds32(sm + slot4(s)) : 0u; }
+    __device__ __forceinline__ float4 get_a(int s) const { return lds128(sa + slot16(s)); }
+    __device__ __forceinline__ float4 get_oa(int s) const { return lds128(soa + slot16(s)); }
+    __device__ __forceinline__ unsigned get_ma(int s) const { return lds32(sma + slot4(s)); }
 
     __device__ __forceinline__ void init(unsigned char* smem, int tid) {
         const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
+        constexpr unsigned F16 = RD * kThreads * 16, F4 = RD * kThreads * 4;
         su = base + tid * 16;
-        sd = su + kRing * kThreads * 16;
-        so = sd + kRing * kThreads * 16;
-        sm = base + 3 * kRing * kThreads * 16 + tid * 4;
+        sd = su + F16;
+        so = sd + F16;
+        sa = so + F16;
+        soa = sa + F16;
+        const unsigned small = base + (PA == 1 ? 5 : 3) * F16 + tid * 4;
+        sm = small;
+        sma = small + F4;
     }
     // Bind the lane's column pointers of one work item.
     __device__ __forceinline__ void bind(const Params& p, const MarchLane& m, const float* x0, const float* dxp) {
-        const int colc = m.lane_ok ? m.col0 : 0, ch = p.ch_a + m.cu;
-        u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + colc;
-        du = HAS_D ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + colc : nullptr;
-        ob = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + colc : nullptr;
-        mk = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + colc : nullptr;
+        const int ch = p.ch_a + m.cu;
+        colc = m.lane_ok ? m.col0 : 0;
+        OBS_L1 = p.obs_l1 != 0;
+        u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc;
+        du = HAS_D ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc : nullptr;
+        ob = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc : nullptr;
+        mk = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc : nullptr;
+        if (PA == 1) {   // the a-plane paired with u-plane cu is a-channel cu
+            a = x0 + (int64_t)m.b * p.x0.sb + (int64_t)m.cu * p.x0.sc;
+            oa = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)m.b * p.obs_a.sb + (int64_t)m.cu * p.obs_a.sc;
+            ma = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)m.b * p.mask_a.sb + (int64_t)m.cu * p.mask_a.sc;
+        }
     }
 };
 
@@ -200,7 +238,7 @@ __device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, 
 // ---------------------------------------------------------------------------------------------------------
 // pass 1 (fast): S_a, S_u, S_pde
 // ---------------------------------------------------------------------------------------------------------
-template <bool HAS_D, bool HAS_O>
+template <bool HAS_D, bool HAS_O, int PA>
 __global__ void __launch_bounds__(kThreads, 2)
 heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g,
                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
@@ -234,7 +272,8 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     // ---- u-planes: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1].
     //      Ring element s is row ys + s:  uc comes from element it+1, dudt / obs / mask from element it.
     const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O> ring;
+    RowRing<HAS_D, HAS_O, PA> ring;
+    constexpr int kRing = ring_depth(PA);
     ring.init(ring_mem, tid);
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
@@ -244,13 +283,20 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
 #pragma unroll
         for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
         const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
-        D4v ua = widen(ldg4(ring.u + row_offset(p, m.ys - 1))), ub = widen(ldg4(ring.u + row_offset(p, m.ys)));
+        D4v ua = widen(ring.direct_u(p, m.ys - 1)), ub = widen(ring.direct_u(p, m.ys));
 #pragma unroll 3
         for (int it = 0; it < n_it; ++it) {
             cp_async_wait<kRing - 2>();                          // elements <= it + 1 have landed
             const D4v uc = widen(ring.get_u(it + 1));
             const float4 dt = ring.get_d(it), o = ring.get_o(it);
             unsigned k = ring.get_m(it);
+            float4 av, oav;
+            unsigned ka = 0u;
+            if (PA == 1) {
+                av = ring.get_a(it);
+                oav = ring.get_oa(it);
+                ka = ring.get_ma(it);
+            }
             const int sn = it + kRing;                           // refill the slot just drained
             ring.issue(p, sn, sn < n_el, sn < n_it, sn < n_it);
             double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
@@ -269,12 +315,18 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
                 const double d2 = u8_to_double((k >> 16) & 255u) * (ub.v[2] - (double)o.z), d3 = u8_to_double(k >> 24) * (ub.v[3] - (double)o.w);
                 s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
             }
+            if (PA == 1) {   // paired a-plane row: sum (mask (a - obs))^2
+                if (!ok) ka = 0u;
+                const double d0 = u8_to_double(ka & 255u) * ((double)av.x - (double)oav.x), d1 = u8_to_double((ka >> 8) & 255u) * ((double)av.y - (double)oav.y);
+                const double d2 = u8_to_double((ka >> 16) & 255u) * ((double)av.z - (double)oav.z), d3 = u8_to_double(ka >> 24) * ((double)av.w - (double)oav.w);
+                s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
             ua = ub;
             ub = uc;
         }
         cp_async_wait<0>();
     };
-    run_interleaved(warp0, nwarps, g.n_warp_items, p.has_a ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+    run_interleaved(warp0, nwarps, g.n_warp_items, (PA == 0 && p.has_a) ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
 
     block_sum3(s_a, s_u, s_p, scratch);
     if (tid == 0) {
@@ -306,7 +358,7 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 (fast): seed gradient
 // ---------------------------------------------------------------------------------------------------------
-template <bool HAS_D, bool HAS_O>
+template <bool HAS_D, bool HAS_O, int PA>
 __global__ void __launch_bounds__(kThreads, 2)
 heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, const double* __restrict__ scal,
                       const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
@@ -352,7 +404,8 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
     //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
     const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O> ring;
+    RowRing<HAS_D, HAS_O, PA> ring;
+    constexpr int kRing = ring_depth(PA);
     ring.init(ring_mem, tid);
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
@@ -362,12 +415,14 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
         // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
 #pragma unroll
         for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
-        const int ch = p.ch_a + m.cu, colc = m.lane_ok ? m.col0 : 0;
-        float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane + colc;
-        float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane + colc : nullptr;
+        const int ch = p.ch_a + m.cu, colc = ring.colc;
+        float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane;                                   // (+ colc at the store)
+        float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane : nullptr;
+        float* gaout = PA ? g_x0 + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;                 // paired a-plane
+        float* gadout = (PA && g_dxdt) ? g_dxdt + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;
         const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
         const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
-        D4v ua = widen(ldg4(ring.u + row_offset(p, m.ys - 2))), ub = widen(ldg4(ring.u + row_offset(p, m.ys - 1)));
+        D4v ua = widen(ring.direct_u(p, m.ys - 2)), ub = widen(ring.direct_u(p, m.ys - 1));
         double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 3
         for (int it = 0; it < n_it; ++it) {
@@ -376,6 +431,13 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
             const D4v uc = widen(ring.get_u(it + 2));
             const float4 dt = ring.get_d(it + 1), o = ring.get_o(it);
             const unsigned k = ring.get_m(it);
+            float4 av, oav;
+            unsigned ka = 0u;
+            if (PA == 1) {
+                av = ring.get_a(it);
+                oav = ring.get_oa(it);
+                ka = ring.get_ma(it);
+            }
             const int sn = it + kRing;
             ring.issue(p, sn, sn < n_it + 2, sn < n_it + 1, sn < n_it);
             double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
@@ -412,10 +474,22 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
                     v2 += c_u * (m2 * (m2 * (ua.v[2] - (double)o.z)));
                     v3 += c_u * (m3 * (m3 * (ua.v[3] - (double)o.w)));
                 }
-                *reinterpret_cast<float4*>(gout + (int64_t)jo * p.W) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+                *reinterpret_cast<float4*>((gout + (int64_t)jo * p.W) + colc) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
                 if (gdout)
-                    *reinterpret_cast<float4*>(gdout + (int64_t)jo * p.W) =
+                    *reinterpret_cast<float4*>((gdout + (int64_t)jo * p.W) + colc) =
                         make_float4((float)(c_p * r1[0]), (float)(c_p * r1[1]), (float)(c_p * r1[2]), (float)(c_p * r1[3]));
+                if (PA) {   // paired a-plane, row jo: g = c_a mask (mask (a - obs)); zeros when mask_a is empty
+                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (PA == 1) {
+                        const double m0 = u8_to_double(ka & 255u), m1 = u8_to_double((ka >> 8) & 255u), m2 = u8_to_double((ka >> 16) & 255u), m3 = u8_to_double(ka >> 24);
+                        w.x = (float)(c_a * (m0 * (m0 * ((double)av.x - (double)oav.x))));
+                        w.y = (float)(c_a * (m1 * (m1 * ((double)av.y - (double)oav.y))));
+                        w.z = (float)(c_a * (m2 * (m2 * ((double)av.z - (double)oav.z))));
+                        w.w = (float)(c_a * (m3 * (m3 * ((double)av.w - (double)oav.w))));
+                    }
+                    *reinterpret_cast<float4*>((gaout + (int64_t)jo * p.W) + colc) = w;
+                    if (gadout) *reinterpret_cast<float4*>((gadout + (int64_t)jo * p.W) + colc) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -427,5 +501,5 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
         }
         cp_async_wait<0>();
     };
-    run_interleaved(warp0, nwarps, g.n_warp_items, g.n_a_items, (tid >> 5) & 1, do_u, do_a);
+    run_interleaved(warp0, nwarps, g.n_warp_items, PA == 0 ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
 }

@@ -87,6 +87,11 @@ const char* dpde_last_error(void);
    every layout.  Both give the same results (tests run both).  Returns the previous setting. */
 int dpde_set_fast_path(int enable);
 
+/* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 = 120
+   columns + 1 halo lane; 1 = 112 + 2, sector aligned), key 1 = 1 disables the warp-uniform kernels, key 2 rows per
+   chunk (0 = automatic), key 3 = 1 keeps a-planes as separate streaming items.  Process-wide, not thread-safe. */
+int dpde_set_tuning(int key, int value);
+
 /* Bytes of scratch the reduce pass needs (per-CTA partial sums + a ticket counter).  The caller zero-fills it
    once after allocation; the library leaves it zeroed-where-needed after every call. */
 size_t dpde_guidance_workspace_bytes(void);

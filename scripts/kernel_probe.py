@@ -14,6 +14,11 @@ nums = [int(a) for a in sys.argv[1:] if a.isdigit()]
 B, H, W = nums if len(nums) == 3 else (8, 4096, 4096)
 llg = "--llg" in sys.argv
 reps = 3
+for a in sys.argv[1:]:                      # --tune=key:value[,key:value...]  (dpde_set_tuning)
+    if a.startswith("--tune="):
+        for kv in a[7:].split(","):
+            k, v = kv.split(":")
+            _ffi.check(_ffi.lib().dpde_set_tuning(int(k), int(v)))
 dev = torch.device("cuda:0")
 C_, ch_a = (6, 3) if llg else (2, 1)
 if "--uonly" in sys.argv:
@@ -62,7 +67,7 @@ for name, kind in kinds:
     timed(f"guidance_vjp[{name}]", 4 * px * (2 * C_ + nd), vjp)
     del eng, hold
 
-if not llg:
+if not llg and "--guidance-only" not in sys.argv:
     n = x0.numel()
     x64 = torch.randn(B, C_, H, W, device=dev, dtype=torch.float64)
     o64, o32 = torch.empty_like(x64), torch.empty_like(x0)

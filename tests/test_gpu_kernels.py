@@ -223,8 +223,9 @@ def test_empty_mask_branches_and_nan_semantics(kernel_path):
     assert torch.isfinite(g2[:, 1]).all()
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 16, 8), (3, 3, 64, 16), (1, 3, 33, 130), (2, 0, 12, 20)])
-def test_llg_norm_guidance(shape):
+@pytest.mark.parametrize("shape", [(2, 3, 16, 8), (3, 3, 64, 16), (1, 3, 33, 130), (2, 0, 12, 20), (2, 3, 70, 132), (3, 3, 128, 128),
+                                   (1, 3, 5, 4100)])
+def test_llg_norm_guidance(shape, kernel_path):
     from dynamical_pde_diffusion_b200 import GuidanceEngine
     from dynamical_pde_diffusion_b200._ffi import PDE_LLG_NORM
 
@@ -248,9 +249,10 @@ def test_llg_norm_guidance(shape):
     assert torch.isfinite(g).all()
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 12, 9), (2, 3, 64, 16), (1, 3, 130, 40), (2, 0, 20, 70)])
+@pytest.mark.parametrize("shape", [(2, 3, 12, 9), (2, 3, 64, 16), (1, 3, 130, 40), (2, 0, 20, 70), (2, 3, 16, 8), (2, 0, 12, 20),
+                                   (1, 3, 70, 132), (3, 3, 128, 128), (1, 3, 20, 36), (2, 3, 2, 4), (1, 3, 3, 260), (1, 0, 66, 64)])
 @pytest.mark.parametrize("K0", [0.0, 5e4])
-def test_llg_residual_guidance(shape, K0):
+def test_llg_residual_guidance(shape, K0, kernel_path):
     from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants
     from dynamical_pde_diffusion_b200._ffi import PDE_LLG_RESIDUAL
 
