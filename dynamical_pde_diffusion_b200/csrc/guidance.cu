@@ -35,7 +35,6 @@ struct Params {
     int B, C, ch_a, H, W, kind, has_a, has_u;
     int Hg, yg0, ylo, yhi;  // row slab: global height, global row of local row 0, owned local rows [ylo, yhi)
     int n_u_units, units_per_sample;
-    int obs_l1;             // marching kernels: fetch observation rows with L1 allocation
     int tile_w, tile_h, tw_log2, tiles_x, tiles_y;
     int64_t tiles_per_plane, n_tiles;
     View x0, dxdt, obs_a, mask_a, obs_u, mask_u;
@@ -574,14 +573,22 @@ laplacian_kernel(const T* __restrict__ u, T* __restrict__ out, int64_t planes, i
 // =========================================================================================================
 bool g_fast_path = true;
 // experiment knobs (dpde_set_tuning): [0] strip layout 0 = 120 columns + 1 halo lane, 1 = 112 + 2 (sector aligned);
-// [1] unused; [2] rows per chunk (0 = automatic); [3] 1 = never pair a-planes in the reduce pass; [4] 1 = pair them in
-// the VJP pass too; [5] 1 = observation rows through L1 (cp.async.ca)
+// [1] unused; [2] rows per chunk (0 = automatic); [3] / [4] 1 = pair a-planes with u-planes in the
+// reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s)
 int g_tuning[8] = {1, 0, 0, 0, 0, 0, 0, 0};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
 
 // Can the row-marching kernels take this problem?  (else the generic tile kernels run)
+// float4 per streaming work item: kABlock on large problems, halved until every SM has ~32 warps' worth of items
+inline int stream_block4(int64_t plane4, int64_t planes) {
+    int blk = kABlock;
+    const int64_t want = (int64_t)sm_count() * 32;
+    while (blk > 32 && ((plane4 + blk - 1) / blk) * planes < want) blk >>= 1;
+    return blk;
+}
+
 bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
     if (!g_fast_path || p.kind != DPDE_PDE_HEAT || p.x0.dtype != DPDE_F32 || p.W % 4 != 0) return false;
     if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * ((p.H + 7) / 8) * ((p.W + 111) / 112) >= (1ll << 30)) return false;
@@ -596,7 +603,7 @@ bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
     return true;
 }
 
-MarchGeom march_geometry(const Params& p) {
+MarchGeom march_geometry(const Params& p, bool vjp) {
     MarchGeom g;
     const int rows = p.yhi - p.ylo;
     if (p.W <= 128) {
@@ -608,10 +615,13 @@ MarchGeom march_geometry(const Params& p) {
         if (g_tuning[0] == 0) { g.strip_w = 120; g.halo_lane = 1; } else { g.strip_w = 112; g.halo_lane = 2; }
         g.strips = (p.W + g.strip_w - 1) / g.strip_w;
     }
-    // rows per chunk: long chunks amortise the 2-row warm-up, short ones expose more warps on small problems
+    // rows per chunk: long chunks amortise the warm-up rows (2 of R + 2 in the reduce pass, 4 of R + 4 in the VJP:
+    // measured on 8x2x4096^2, VJP 4.41 / 4.53 / 4.73 TB/s at R = 32 / 64 / 128, reduce best at 64), short ones expose
+    // more warps on small problems: take the longest chunk that still leaves two items per resident warp.
     const int64_t per_row_items = (int64_t)g.strips * p.n_u_units * p.B;
     const int64_t want_warps = (int64_t)sm_count() * 16;
-    int R = 32;
+    int R = vjp ? 128 : 64;
+    while (R > 32 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < 2 * want_warps) R >>= 1;
     while (R > 8 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
     if (g_tuning[2] > 0) R = g_tuning[2];
     g.R = R;
@@ -619,14 +629,15 @@ MarchGeom march_geometry(const Params& p) {
     g.n_seg_items = (int)((int64_t)g.chunks * per_row_items);
     g.n_warp_items = (g.n_seg_items + g.segs_per_warp - 1) / g.segs_per_warp;
     g.a_plane4 = (int)((int64_t)rows * p.W / 4);
-    g.a_blocks_per_plane = (g.a_plane4 + kABlock - 1) / kABlock;
+    g.a_block4 = stream_block4(g.a_plane4, (int64_t)(p.ch_a > 0 ? p.ch_a : 1) * p.B);
+    g.a_blocks_per_plane = (g.a_plane4 + g.a_block4 - 1) / g.a_block4;
     g.n_a_items = g.a_blocks_per_plane * p.ch_a * p.B;
     return g;
 }
 
 // 0: a-planes are separate streaming items; 1: paired with the u-plane of the same index; 2: paired, mask_a empty
 inline int pairing(const Params& p, bool vjp) {
-    return ((vjp ? g_tuning[4] != 0 : g_tuning[3] == 0) && p.ch_a >= 1 && p.ch_a == p.n_u_units) ? (p.has_a ? 1 : 2) : 0;
+    return ((vjp ? g_tuning[4] != 0 : g_tuning[3] != 0) && p.ch_a >= 1 && p.ch_a == p.n_u_units) ? (p.has_a ? 1 : 2) : 0;
 }
 
 template <typename K>
@@ -661,7 +672,7 @@ int launch_march_reduce_pa(const Params& p, const MarchGeom& g, double* partials
 template <bool HAS_D, bool HAS_O>
 int launch_march_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal,
                         float* trace, cudaStream_t s) {
-    const MarchGeom g = march_geometry(p);
+    const MarchGeom g = march_geometry(p, false);
     switch (pairing(p, false)) {
         case 1: return launch_march_reduce_pa<HAS_D, HAS_O, 1>(p, g, partials, ticket, sums, finalize, scal, trace, s);
         case 2: return launch_march_reduce_pa<HAS_D, HAS_O, 2>(p, g, partials, ticket, sums, finalize, scal, trace, s);
@@ -680,7 +691,7 @@ int launch_march_vjp_pa(const Params& p, const MarchGeom& g, const double* scal,
 
 template <bool HAS_D, bool HAS_O>
 int launch_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
-    const MarchGeom g = march_geometry(p);
+    const MarchGeom g = march_geometry(p, true);
     switch (pairing(p, true)) {
         case 1: return launch_march_vjp_pa<HAS_D, HAS_O, 1>(p, g, scal, upstream, g_x0, g_dxdt, s);
         case 2: return launch_march_vjp_pa<HAS_D, HAS_O, 2>(p, g, scal, upstream, g_x0, g_dxdt, s);
@@ -717,7 +728,8 @@ LlgGeom llg_geometry(const Params& p) {
     L.tiles_x = (p.W + L.tw - 1) / L.tw;
     L.n_tiles = p.B * ((rows + th - 1) / th) * L.tiles_x;
     L.g.a_plane4 = (int)((int64_t)rows * p.W / 4);
-    L.g.a_blocks_per_plane = (L.g.a_plane4 + kABlock - 1) / kABlock;
+    L.g.a_block4 = stream_block4(L.g.a_plane4, p.B);
+    L.g.a_blocks_per_plane = (L.g.a_plane4 + L.g.a_block4 - 1) / L.g.a_block4;
     L.g.n_a_items = L.g.a_blocks_per_plane * p.ch_a * p.B;
     L.n_norm_items = L.g.a_blocks_per_plane * p.B;
     return L;
@@ -835,7 +847,6 @@ int validate_and_fill(const dpde_guidance_desc* d, int tile_pix, Params& p, cons
     p.has_a = d->has_a != 0; p.has_u = d->has_u != 0;
     const bool llg = d->pde_kind == DPDE_PDE_LLG_NORM || d->pde_kind == DPDE_PDE_LLG_RESIDUAL;
     p.n_u_units = llg ? 1 : cu;
-    p.obs_l1 = g_tuning[5];
     p.units_per_sample = d->ch_a + p.n_u_units;
     p.tile_w = d->W > 64 ? 128 : d->W > 32 ? 64 : d->W > 16 ? 32 : 16;
     p.tile_h = tile_pix / p.tile_w;

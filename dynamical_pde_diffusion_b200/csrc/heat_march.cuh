@@ -32,9 +32,10 @@ struct MarchGeom {
     int n_seg_items, n_warp_items;       // u-plane work: row segments, and warps' worth of them
     int a_blocks_per_plane, n_a_items;   // a-plane work: blocks of kABlock float4 within one plane's owned rows
     int a_plane4;                        // float4 per a-plane (owned rows)
+    int a_block4;                        // float4 per a-plane work item (kABlock, smaller on small problems)
 };
 
-constexpr int kABlock = 1024;            // float4 per a-plane work item (4096 pixels)
+constexpr int kABlock = 1024;            // largest a-plane work item, in float4 (4096 pixels)
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uchar4 ldg4(const unsigned char* p) { return __ldg(reinterpret_cast<const uchar4*>(p)); }
@@ -50,11 +51,6 @@ __host__ __device__ constexpr int ring_bytes(int PA) { return ring_depth(PA) * k
 // conversion otherwise costs ~6 instructions per copy)
 __device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
-}
-// .ca: allocate in L1.  Observation / mask rows are broadcast over the batch and the warps of a CTA work on
-// consecutive samples of the same tile, so all but the first reader hit in L1 and never cross the L2 crossbar.
-__device__ __forceinline__ void cp_async16_ca(unsigned smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async4(unsigned smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
@@ -126,7 +122,6 @@ struct RowRing {
     const float *u, *du, *ob, *a, *oa;
     const unsigned char *mk, *ma;
     int row0;
-    bool OBS_L1;                             // observation rows through L1 (they broadcast over the batch)
 
     static __device__ __forceinline__ unsigned slot16(int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); }
     static __device__ __forceinline__ unsigned slot4(int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); }
@@ -136,22 +131,20 @@ struct RowRing {
     int colc;                                // the lane's first column (clamped to 0 for idle lanes)
     __device__ __forceinline__ void issue(const Params& p, int s, bool fu, bool fd, bool fo) const {
         const int off = row_offset(p, row0 + s);
-        if (fu) cp_async16(su + slot16(s), (u + off) + colc);
-        if (HAS_D && fd) cp_async16(sd + slot16(s), (du + off) + colc);
+        if (fu) cp_async16(su + slot16(s), u + off);
+        if (HAS_D && fd) cp_async16(sd + slot16(s), du + off);
         if (HAS_O && fo) {
-            if (OBS_L1) cp_async16_ca(so + slot16(s), (ob + off) + colc);
-            else cp_async16(so + slot16(s), (ob + off) + colc);
-            cp_async4(sm + slot4(s), (mk + off) + colc);
+            cp_async16(so + slot16(s), ob + off);
+            cp_async4(sm + slot4(s), mk + off);
         }
         if (PA == 1 && fo) {
-            cp_async16(sa + slot16(s), (a + off) + colc);
-            if (OBS_L1) cp_async16_ca(soa + slot16(s), (oa + off) + colc);
-            else cp_async16(soa + slot16(s), (oa + off) + colc);
-            cp_async4(sma + slot4(s), (ma + off) + colc);
+            cp_async16(sa + slot16(s), a + off);
+            cp_async16(soa + slot16(s), oa + off);
+            cp_async4(sma + slot4(s), ma + off);
         }
         cp_async_commit();
     }
-    __device__ __forceinline__ float4 direct_u(const Params& p, int y) const { return ldg4((u + row_offset(p, y)) + colc); }
+    __device__ __forceinline__ float4 direct_u(const Params& p, int y) const { return ldg4(u + row_offset(p, y)); }
     __device__ __forceinline__ float4 get_u(int s) const { return lds128(su + slot16(s)); }
     __device__ __forceinline__ float4 get_d(int s) const { return HAS_D ? lds128(sd + slot16(s)) : make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ float4 get_o(int s) const { return HAS_O ? lds128(so + slot16(s)) : make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -176,15 +169,15 @@ struct RowRing {
     __device__ __forceinline__ void bind(const Params& p, const MarchLane& m, const float* x0, const float* dxp) {
         const int ch = p.ch_a + m.cu;
         colc = m.lane_ok ? m.col0 : 0;
-        OBS_L1 = p.obs_l1 != 0;
-        u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc;
-        du = HAS_D ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc : nullptr;
-        ob = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc : nullptr;
-        mk = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc : nullptr;
+        // every pointer already includes the lane's column, so one row offset serves all copies of an element
+        u = x0 + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + colc;
+        du = HAS_D ? dxp + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + colc : nullptr;
+        ob = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + colc : nullptr;
+        mk = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + colc : nullptr;
         if (PA == 1) {   // the a-plane paired with u-plane cu is a-channel cu
-            a = x0 + (int64_t)m.b * p.x0.sb + (int64_t)m.cu * p.x0.sc;
-            oa = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)m.b * p.obs_a.sb + (int64_t)m.cu * p.obs_a.sc;
-            ma = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)m.b * p.mask_a.sb + (int64_t)m.cu * p.mask_a.sc;
+            a = x0 + (int64_t)m.b * p.x0.sb + (int64_t)m.cu * p.x0.sc + colc;
+            oa = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)m.b * p.obs_a.sb + (int64_t)m.cu * p.obs_a.sc + colc;
+            ma = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)m.b * p.mask_a.sb + (int64_t)m.cu * p.mask_a.sc + colc;
         }
     }
 };
@@ -209,8 +202,8 @@ __device__ __forceinline__ AItem a_decode(const Params& p, const MarchGeom& g, i
     a.b = (int)((unsigned)item - t * p.B);
     const unsigned blk = t / (unsigned)p.ch_a;
     a.ch = (int)(t - blk * p.ch_a);
-    a.first4 = (int)blk * kABlock;
-    a.n4 = min(kABlock, g.a_plane4 - a.first4);
+    a.first4 = (int)blk * g.a_block4;
+    a.n4 = min(g.a_block4, g.a_plane4 - a.first4);
     return a;
 }
 

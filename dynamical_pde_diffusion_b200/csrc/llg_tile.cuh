@@ -564,8 +564,8 @@ __device__ __forceinline__ NormItem norm_decode(const Params& p, const MarchGeom
     const unsigned blk = (unsigned)item / (unsigned)p.B;
     NormItem n;
     n.b = (int)((unsigned)item - blk * p.B);
-    n.first4 = (int)blk * kABlock;
-    n.n4 = min(kABlock, g.a_plane4 - n.first4);
+    n.first4 = (int)blk * g.a_block4;
+    n.n4 = min(g.a_block4, g.a_plane4 - n.first4);
     return n;
 }
 

@@ -13,7 +13,7 @@ from dynamical_pde_diffusion_b200._ffi import PDE_HEAT, PDE_LLG_NORM, PDE_LLG_RE
 nums = [int(a) for a in sys.argv[1:] if a.isdigit()]
 B, H, W = nums if len(nums) == 3 else (8, 4096, 4096)
 llg = "--llg" in sys.argv
-reps = 3
+reps = 10
 for a in sys.argv[1:]:                      # --tune=key:value[,key:value...]  (dpde_set_tuning)
     if a.startswith("--tune="):
         for kv in a[7:].split(","):
@@ -32,9 +32,25 @@ obs_a, obs_u = torch.randn(1, max(ch_a, 1), H, W, device=dev), torch.randn(1, cu
 w = (20.0, 0.5, 20.0)
 
 
+loop = 0
+for a in sys.argv[1:]:
+    if a.startswith("--loop="):
+        loop = int(a[7:])
+
+
 def timed(label, nbytes, fn):
     fn()
     torch.cuda.synchronize()
+    if loop:                                 # back-to-back launches: steady-state (L2-warm) cost per launch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(loop):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / loop
+        print(f"{label:34s} {ms * 1e3:8.2f} us/launch (x{loop} back to back)  {nbytes / ms / 1e6:8.1f} GB/s (algorithmic)")
+        return
     ts = []
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -43,7 +59,7 @@ def timed(label, nbytes, fn):
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    ms = sum(ts) / len(ts)
+    ms = sorted(ts)[len(ts) // 2]
     print(f"{label:34s} {ms:8.4f} ms  {nbytes / ms / 1e6:8.1f} GB/s (algorithmic)")
 
 
