@@ -591,7 +591,7 @@ inline int stream_block4(int64_t plane4, int64_t planes) {
 
 bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
     if (!g_fast_path || p.kind != DPDE_PDE_HEAT || p.x0.dtype != DPDE_F32 || p.W % 4 != 0) return false;
-    if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * ((p.H + 7) / 8) * ((p.W + 111) / 112) >= (1ll << 30)) return false;
+    if ((int64_t)p.H * p.W >= (1ll << 30) || (int64_t)p.B * p.C * ((p.H + 3) / 4) * ((p.W + 111) / 112) >= (1ll << 30)) return false;
     if (!al(p.x0.p, 16) || !s4(p.x0)) return false;
     if (p.dxdt.p && (!al(p.dxdt.p, 16) || !s4(p.dxdt))) return false;
     if (g_x0 && !al(g_x0, 16)) return false;
@@ -622,7 +622,7 @@ MarchGeom march_geometry(const Params& p, bool vjp) {
     const int64_t want_warps = (int64_t)sm_count() * 16;
     int R = vjp ? 128 : 64;
     while (R > 32 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < 2 * want_warps) R >>= 1;
-    while (R > 8 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
+    while (R > 4 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
     if (g_tuning[2] > 0) R = g_tuning[2];
     g.R = R;
     g.chunks = (rows + R - 1) / R;

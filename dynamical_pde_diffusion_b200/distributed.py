@@ -123,3 +123,50 @@ def sweep_work_items(zeta_values, step_counts, total_samples, chunk):
 
 def my_items(items, world: int, rank: int):
     return items[rank::world]
+
+
+def run_sweep(make_sampler, problem, zeta_values, step_counts, total_samples, chunk, *, group=None, seed=0,
+              reduce_device=None):
+    """Config 4 -- the zeta / num-steps sensitivity sweep (the reference does it one call at a time in
+    ``notebooks/sampler_hyperparameter_opt.ipynb``).
+
+    ``make_sampler(num_samples, num_steps)`` returns a sampler with the ``JointSampler.sample`` signature;
+    ``problem`` holds ``labels`` (1, L) (expanded to the chunk, ``model_testing.py:195-196``), ``obs_a``, ``obs_u``,
+    ``mask_a``, ``mask_u``; ``zeta_values`` is a list of ``(zeta_a, zeta_u, zeta_pde)``.  The work items
+    ``(zeta index, num_steps, first sample, n samples)`` are dealt round-robin to the ranks and run independently (a chunk is
+    one reference call of batch ``n``, so results do not depend on the world size); the only collective is ONE
+    all-reduce of the per-item summaries at the end.
+
+    Returns ``(final_losses, n_done)``: ``final_losses[z, s]`` = the last loss-trace row ``[loss_a, loss_u, loss_pde,
+    loss_comb]`` averaged over the chunks of (zeta z, step count s), shape ``(len(zeta_values), len(step_counts), 4)``,
+    identical on every rank; ``n_done`` = sample-steps this rank executed (for throughput accounting).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    items = sweep_work_items(zeta_values, step_counts, total_samples, chunk)
+    step_index = {n: k for k, n in enumerate(step_counts)}
+    acc = torch.zeros((len(zeta_values), len(step_counts), 5), dtype=torch.float64)   # 4 loss sums + chunk count
+    samplers, n_done = {}, 0
+    for zi, n_steps, s0, n in my_items(items, world, rank):
+        key = (n, n_steps)
+        if key not in samplers:
+            samplers[key] = make_sampler(n, n_steps)
+        labels = problem["labels"]
+        if labels is not None:
+            labels = labels.expand(n, -1)
+        za, zu, zp = zeta_values[zi]
+        gen_seed = seed + 1000003 * zi + 7919 * n_steps + s0          # every chunk has its own reproducible latents
+        lat = full_latents(n, samplers[key].num_channels, samplers[key].sample_shape, gen_seed)
+        _, trace = samplers[key].sample(labels, problem["obs_a"], problem["obs_u"], problem["mask_a"], problem["mask_u"],
+                                        za, zu, zp, return_losses=True, num_steps=n_steps, latents=lat)
+        acc[zi, step_index[n_steps], :4] += torch.as_tensor(np.asarray(trace[-1], dtype=np.float64))
+        acc[zi, step_index[n_steps], 4] += 1.0
+        n_done += n * n_steps
+    if world > 1:
+        dev = reduce_device if reduce_device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+        t = acc.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        acc = t.cpu()
+    final = (acc[..., :4] / acc[..., 4:].clamp_min(1.0)).numpy()
+    return final, n_done

@@ -106,6 +106,73 @@ def _f32c(t):
 class Sampler:
     """Base class, as in the reference (``sample.py:137-143``)."""
 
+    # ---- schedule (sample.py:206-209, 305-308) -----------------------------------------------------------
+    def _sigmas(self, num_steps, sigma_min, sigma_max, rho):
+        idx = torch.arange(num_steps, dtype=F64, device=self.device)
+        s = (sigma_max ** (1.0 / rho) + idx / (num_steps - 1) * (sigma_min ** (1.0 / rho) - sigma_max ** (1.0 / rho))) ** rho
+        s = getattr(self.net, "round_sigma", lambda v: v)(s)
+        return torch.cat([s, torch.zeros_like(s[:1])]).tolist()      # one D2H per sample() call
+
+
+class UnconditionalSampler(Sampler):
+    """EDM Heun sampler without guidance, with the reference's API (``sample.py:145-239``), on the same kernels as
+    the guided sampler: ``dpde_sampler_init`` (latents * sigma_0 + the fp32 copy the denoiser reads),
+    ``dpde_euler_predict`` (the fp32 Euler state of the second evaluation) and ``dpde_heun_guided_update`` with no
+    gradient operands.  The fp64 state never leaves the device and nothing synchronises the host inside the loop."""
+
+    def __init__(self, net, device, sample_shape, num_channels, num_samples, num_steps=18, sigma_min=0.002, sigma_max=80.0,
+                 rho=7.0):
+        self.net = net
+        self.device = device
+        self.sample_shape = sample_shape
+        self.num_channels = num_channels
+        self.num_samples = num_samples
+        self.num_steps = num_steps
+        self.sigma_min = sigma_min
+        self.sigma_max = sigma_max
+        self.rho = rho
+        self.dtype_f = F32
+        self.dtype_t = F64
+
+    @torch.no_grad()
+    def sample(self, labels=None, net_obs=None, num_steps=None, sigma_min=None, sigma_max=None, rho=None, *, latents=None,
+               generator=None):
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"dpde_b200.UnconditionalSampler runs on CUDA devices only (got {dev}); there is no CPU path")
+        num_steps = num_steps if num_steps is not None else self.num_steps
+        sigma_min = sigma_min if sigma_min is not None else self.sigma_min
+        sigma_max = sigma_max if sigma_max is not None else self.sigma_max
+        rho = rho if rho is not None else self.rho
+        sigmas = self._sigmas(num_steps, sigma_min, sigma_max, rho)
+        B = labels.shape[0] if labels is not None else self.num_samples
+        if labels is not None:
+            labels = labels.to(device=dev, dtype=F32)
+        args = (labels,)
+        if net_obs is not None:
+            args = (labels, net_obs.to(device=dev, dtype=F32))
+        shape = (B, self.num_channels, *self.sample_shape)
+        if latents is None:   # first RNG call, as sample.py:222
+            latents = torch.randn(shape, device=dev, dtype=F64, generator=generator)
+        else:
+            latents = latents.to(device=dev, dtype=F64).contiguous()
+        x64, x64n = torch.empty(shape, dtype=F64, device=dev), torch.empty(shape, dtype=F64, device=dev)
+        x32, x_eu = torch.empty(shape, dtype=F32, device=dev), torch.empty(shape, dtype=F32, device=dev)
+        n, st = x64.numel(), _stream()
+        _ffi.call("dpde_sampler_init", latents.data_ptr(), sigmas[0], x64.data_ptr(), x32.data_ptr(), n, st)
+        for i in range(num_steps):
+            s_cur, s_next = sigmas[i], sigmas[i + 1]
+            x0_1 = _f32c(self.net(x32, torch.full((B,), s_cur, device=dev, dtype=F32), *args))
+            x0_2 = None
+            if i < num_steps - 1:
+                _ffi.call("dpde_euler_predict", x64.data_ptr(), x0_1.data_ptr(), s_cur, s_next, x_eu.data_ptr(), n, st)
+                x0_2 = _f32c(self.net(x_eu, torch.full((B,), s_next, device=dev, dtype=F32), *args))
+            x32n = torch.empty_like(x32)
+            _ffi.call("dpde_heun_guided_update", x64.data_ptr(), x0_1.data_ptr(), x0_2.data_ptr() if x0_2 is not None else None,
+                      None, None, s_cur, s_next, x64n.data_ptr(), x32n.data_ptr(), n, st)
+            x64, x64n, x32 = x64n, x64, x32n
+        return x32.detach().cpu()
+
 
 class JointSampler(Sampler):
     """Physics-guided EDM Heun sampler with the reference's API (``sample.py:243-363``)."""
@@ -130,13 +197,6 @@ class JointSampler(Sampler):
         self.dtype_t = F64   # state and schedule in fp64 (sample.py:275-276)
         self.group, self.coupled = group, coupled
         self._run = None
-
-    # ---- schedule (sample.py:305-308) ------------------------------------------------------------------
-    def _sigmas(self, num_steps, sigma_min, sigma_max, rho):
-        idx = torch.arange(num_steps, dtype=F64, device=self.device)
-        s = (sigma_max ** (1.0 / rho) + idx / (num_steps - 1) * (sigma_min ** (1.0 / rho) - sigma_max ** (1.0 / rho))) ** rho
-        s = getattr(self.net, "round_sigma", lambda v: v)(s)
-        return torch.cat([s, torch.zeros_like(s[:1])]).tolist()      # one D2H per sample() call
 
     def _allreduce(self):
         if not self.coupled:
@@ -274,17 +334,21 @@ class JointSampler(Sampler):
         gd = grads[1].to(F32) if want_d and len(grads) > 1 and grads[1] is not None else None
         return g.to(F32), gd
 
-    def finish(self, return_losses=False):
+    def finish(self, return_losses=False, to_cpu=True):
         r = self._run
-        x = r["x32"].detach().cpu()                                   # fp32 at sigma = 0 (sample.py:360)
+        x = r["x32"].detach()                                         # fp32 at sigma = 0 (sample.py:360)
+        if to_cpu:                                                    # the reference always returns a CPU tensor
+            x = x.cpu()
         losses = r["trace"].cpu().numpy() if return_losses else None  # (N,4) numpy (sample.py:362)
         self._run = None
         return x, losses
 
     def sample(self, labels, obs_a, obs_u, mask_a, mask_u, zeta_a, zeta_u, zeta_pde, return_losses=False,
-               num_steps=None, sigma_min=None, sigma_max=None, rho=None, *, latents=None, generator=None):
+               num_steps=None, sigma_min=None, sigma_max=None, rho=None, *, latents=None, generator=None, to_cpu=True):
+        """``sample.py:278-363``.  Additive keywords: ``latents`` / ``generator`` replace the ``torch.randn`` draw,
+        ``to_cpu=False`` leaves the samples on the device (``evaluation.test_loop`` computes its metrics there)."""
         run = self.begin(labels, obs_a, obs_u, mask_a, mask_u, zeta_a, zeta_u, zeta_pde, num_steps, sigma_min, sigma_max,
                          rho, latents, generator)
         for _ in range(run["N"]):
             self.step()
-        return self.finish(return_losses)
+        return self.finish(return_losses, to_cpu)

@@ -276,6 +276,32 @@ def joint_sample(net, device, sample_shape, num_channels, ch_a, loss_fn, loss_kw
     return x, losses.numpy()
 
 
+def unconditional_sample(net, device, sample_shape, num_channels, labels=None, net_obs=None, num_steps=18, sigma_min=0.002,
+                         sigma_max=80.0, rho=7.0, num_samples=None, latents=None):
+    """Restatement of UnconditionalSampler.sample (sample.py:191-239): plain EDM Heun sampling, fp64 state and
+    schedule, fp32 denoiser.  ``latents`` replaces the reference's ``torch.randn`` draw (sample.py:222)."""
+    sigmas = karras_sigmas(num_steps, sigma_min, sigma_max, rho, device, net)
+    B = labels.shape[0] if labels is not None else num_samples
+    if labels is not None:
+        labels = labels.to(device=device, dtype=F32)
+    args = (labels,) if net_obs is None else (labels, net_obs.to(device=device, dtype=F32))
+    if latents is None:
+        latents = torch.randn((B, num_channels, *sample_shape), device=device, dtype=F64)
+    x_next = latents.to(device=device, dtype=F64) * sigmas[0]
+    with torch.no_grad():
+        for i in range(num_steps):
+            s_cur, s_next = sigmas[i], sigmas[i + 1]
+            x_cur = x_next
+            x_N = net(x_cur.to(F32), torch.full((B,), s_cur, device=device, dtype=F32), *args).to(F64)
+            d_cur = (x_cur - x_N) / s_cur
+            x_next = x_cur + (s_next - s_cur) * d_cur
+            if i < num_steps - 1:
+                x_N = net(x_next.to(F32), torch.full((B,), s_next, device=device, dtype=F32), *args).to(F64)
+                d_prime = (x_next - x_N) / s_next
+                x_next = x_cur + (s_next - s_cur) * (0.5 * d_cur + 0.5 * d_prime)
+    return x_next.to(F32).detach().cpu()
+
+
 # ----------------------------------------------------------------------------------------
 # closed-form seed gradients (numpy, fp64) -- what the CUDA VJP kernels implement
 # ----------------------------------------------------------------------------------------

@@ -139,12 +139,34 @@ def golden_joint(S, PL, M):
     np.savez_compressed(os.path.join(OUT, "joint_llg.npz"), **out)
 
 
+def golden_unconditional(S, M):
+    """UnconditionalSampler.sample (sample.py:145-239) with the denoiser of joint_heat.npz (same seed -> same weights)."""
+    torch.use_deterministic_algorithms(True)
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(17)
+    H, W, B, N = 16, 12, 3, 9
+    net = _tiny_net(M, 2, 2, seed=21)
+    labels = torch.stack([0.5 * torch.rand(B, generator=g), torch.exp(-2.5 + 3 * torch.rand(B, generator=g))], 1).float()
+    torch.manual_seed(8)
+    latents = torch.randn((B, 2, H, W), dtype=torch.float64)          # what sample.py:222 will draw
+    sampler = S.UnconditionalSampler(net=net, device=torch.device("cpu"), sample_shape=(H, W), num_channels=2, num_samples=B,
+                                     num_steps=N)
+    torch.manual_seed(8)
+    x = sampler.sample(labels=labels)
+    np.savez_compressed(os.path.join(OUT, "unconditional_heat.npz"), latents=_np(latents), x=_np(x), labels=_np(labels),
+                        num_steps=np.int64(N))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     S, PL, M = import_reference()
+    if "--only-unconditional" in sys.argv:
+        golden_unconditional(S, M)
+        return
     golden_laplacian(S)
     golden_pde_losses(PL)
     golden_joint(S, PL, M)
+    golden_unconditional(S, M)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -19,6 +19,8 @@ for a in sys.argv[1:]:                      # --tune=key:value[,key:value...]  (
         for kv in a[7:].split(","):
             k, v = kv.split(":")
             _ffi.check(_ffi.lib().dpde_set_tuning(int(k), int(v)))
+if "--generic" in sys.argv:
+    _ffi.lib().dpde_set_fast_path(0)
 dev = torch.device("cuda:0")
 C_, ch_a = (6, 3) if llg else (2, 1)
 if "--uonly" in sys.argv:
@@ -36,6 +38,8 @@ loop = 0
 for a in sys.argv[1:]:
     if a.startswith("--loop="):
         loop = int(a[7:])
+    if a.startswith("--reps="):
+        reps = int(a[7:])
 
 
 def timed(label, nbytes, fn):

@@ -114,6 +114,39 @@ def test_sweep_items_partition():
     assert sum(n for *_, n in items) == 8 * 3 * 4096
 
 
+class _StubSampler:
+    """Stands in for JointSampler on CPU: the last trace row encodes the call so the sweep's bookkeeping can be checked."""
+    num_channels, sample_shape = 2, (4, 4)
+
+    def __init__(self, n, n_steps):
+        self.n, self.n_steps = n, n_steps
+
+    def sample(self, labels, obs_a, obs_u, mask_a, mask_u, za, zu, zp, return_losses=False, num_steps=None, latents=None):
+        assert labels.shape[0] == self.n and latents.shape == (self.n, 2, 4, 4) and num_steps == self.n_steps
+        tr = np.zeros((num_steps, 4), np.float32)
+        tr[-1] = [za, zu, zp, float(latents.double().mean())]
+        return torch.zeros(self.n, 2, 4, 4), tr
+
+
+def _sweep_job(rank, world):
+    zetas = [(1.0 * k, 0.5, 2.0 * k) for k in range(1, 4)]
+    prob = dict(labels=torch.tensor([[0.1, 0.2]]), obs_a=None, obs_u=None, mask_a=None, mask_u=None)
+    final, n_done = D.run_sweep(lambda n, s: _StubSampler(n, s), prob, zetas, (3, 5), 10, 4, seed=1)
+    return final, n_done
+
+
+def test_run_sweep_is_independent_of_world_size():
+    ref, n1 = _sweep_job(0, 1)                         # no process group: single rank
+    assert ref.shape == (3, 2, 4) and n1 == 3 * (3 + 5) * 10
+    np.testing.assert_allclose(ref[:, 0, 0], [1.0, 2.0, 3.0])
+    np.testing.assert_allclose(ref[:, 1, 2], [2.0, 4.0, 6.0])
+    for world in (2, 3):
+        outs = _run(world, _sweep_job)
+        assert sum(o[1] for o in outs) == n1
+        for final, _ in outs:
+            np.testing.assert_allclose(final, ref, rtol=1e-12)
+
+
 # ---- row slabs ---------------------------------------------------------------------------------------------
 def test_slab_plan_rows_and_take():
     H, W = 11, 5

@@ -83,6 +83,29 @@ def test_heat_golden_and_same_device_oracle():
     assert _rel(x.numpy(), xo.numpy()) < SAME, _rel(x.numpy(), xo.numpy())
 
 
+def test_unconditional_sampler_golden_and_same_device_oracle():
+    """UnconditionalSampler (sample.py:145-239) on the fused init / predictor / update kernels."""
+    import dynamical_pde_diffusion_b200 as dp
+
+    gold, u = load_golden("joint_heat.npz"), load_golden("unconditional_heat.npz")
+    net = net_from_golden(gold, 2, 2, device=_dev())
+    labels, lat, N = torch.from_numpy(u["labels"]), torch.from_numpy(u["latents"]), int(u["num_steps"])
+    smp = dp.UnconditionalSampler(net, _dev(), (16, 12), 2, 3, num_steps=N)
+    x = smp.sample(labels=labels, latents=lat)
+    assert isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.dtype == torch.float32 and x.shape == (3, 2, 16, 12)
+    assert _rel(x.numpy(), u["x"]) < XDEV
+    xo = R.unconditional_sample(net, _dev(), (16, 12), 2, labels=labels, num_steps=N, latents=lat)
+    assert torch.equal(x, xo), _rel(x.numpy(), xo.numpy())      # same denoiser kernels + bit-exact update kernels
+    # default latents are the first RNG draw (sample.py:222)
+    torch.manual_seed(3)
+    x1 = smp.sample(labels=labels)
+    torch.manual_seed(3)
+    lat1 = torch.randn((3, 2, 16, 12), device=_dev(), dtype=torch.float64)
+    assert torch.equal(x1, smp.sample(labels=labels, latents=lat1))
+    with pytest.raises(RuntimeError):
+        dp.UnconditionalSampler(net, torch.device("cpu"), (16, 12), 2, 3).sample(labels=labels)
+
+
 def test_heat_empty_mask_golden():
     import dynamical_pde_diffusion_b200 as dp
 
@@ -188,6 +211,31 @@ def test_default_latents_are_the_first_rng_draw():
     for attr in ("net", "device", "num_channels", "sample_shape", "num_samples", "ch_a", "loss_fn", "loss_kwargs",
                  "num_steps", "sigma_min", "sigma_max", "rho", "out_and_grad_fun", "dtype_f", "dtype_t"):
         assert hasattr(smp, attr), attr                                           # sample.py:261-276
+
+
+def test_run_sweep_equals_direct_calls():
+    """Config 4 driver (distributed.run_sweep) on one GPU: every (zeta, num_steps, chunk) item is one plain sample() call."""
+    import dynamical_pde_diffusion_b200 as dp
+    from dynamical_pde_diffusion_b200 import distributed as D
+
+    gold = load_golden("joint_heat.npz")
+    net = net_from_golden(gold, 2, 2, device=_dev())
+    H, W = 16, 12
+    prob = dict(labels=torch.from_numpy(gold["labels"][:1]), obs_a=torch.from_numpy(gold["obs_a"]), obs_u=torch.from_numpy(gold["obs_u"]),
+                mask_a=torch.from_numpy(gold["mask_a"]), mask_u=torch.from_numpy(gold["mask_u"]))
+    zetas, steps = [(20.0, 0.5, 20.0), (2.0, 0.1, 5.0)], (3, 5)
+    make = lambda n, N: dp.JointSampler(net, _dev(), (H, W), 2, n, 1, dp.heat_loss2, {"dx": float(gold["dx"])}, num_steps=N)
+    final, n_done = D.run_sweep(make, prob, zetas, steps, total_samples=4, chunk=2, seed=3)
+    assert final.shape == (2, 2, 4) and n_done == 2 * (3 + 5) * 4
+    for zi, z in enumerate(zetas):
+        for si, N in enumerate(steps):
+            rows = []
+            for s0 in (0, 2):
+                lat = D.full_latents(2, 2, (H, W), 3 + 1000003 * zi + 7919 * N + s0)
+                _, tr = make(2, N).sample(prob["labels"].expand(2, -1), prob["obs_a"], prob["obs_u"], prob["mask_a"], prob["mask_u"],
+                                          *z, return_losses=True, latents=lat)
+                rows.append(tr[-1].astype(np.float64))
+            np.testing.assert_allclose(final[zi, si], np.mean(rows, axis=0), rtol=1e-6)
 
 
 def test_sampler_refuses_cpu():

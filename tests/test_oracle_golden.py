@@ -81,6 +81,15 @@ def test_joint_llg_trajectory():
     np.testing.assert_allclose(x.numpy(), gold["x"], rtol=1e-4, atol=1e-5)
 
 
+def test_unconditional_trajectory():
+    gold, u = load_golden("joint_heat.npz"), load_golden("unconditional_heat.npz")
+    torch.set_num_threads(1)
+    net = net_from_golden(gold, 2, 2)
+    x = R.unconditional_sample(net, torch.device("cpu"), (16, 12), 2, labels=torch.from_numpy(u["labels"]),
+                               num_steps=int(u["num_steps"]), latents=torch.from_numpy(u["latents"]))
+    np.testing.assert_allclose(x.numpy(), u["x"], rtol=1e-5, atol=1e-6)
+
+
 def test_weight_switch_and_schedule():
     # i <= 0.8 N in Python floats (sample.py:348): N=20 -> steps 17..19 reduced; N=50 -> 41..; N=200 -> 161..
     for N, first in [(20, 17), (50, 41), (200, 161), (12, 10)]:
