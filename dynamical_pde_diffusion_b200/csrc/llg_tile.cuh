@@ -588,11 +588,21 @@ llg_norm_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__
         const float* m0 = reinterpret_cast<const float*>(p.x0.p) + (int64_t)it.b * p.x0.sb + (int64_t)p.ch_a * p.x0.sc + base;
         const float* po = p.has_u ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)it.b * p.obs_u.sb + base : nullptr;
         const unsigned char* pm = p.has_u ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)it.b * p.mask_u.sb + base : nullptr;
-#pragma unroll 2
+        // software pipeline: the next iteration's magnetisation is in flight while this one's square roots run
+        float4 nx[3];
+        if (lane < it.n4) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * lane);
+        }
+#pragma unroll 1
         for (int i = lane; i < it.n4; i += 32) {
             double mv[3][4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) widen4(ldg4(m0 + c * p.x0.sc + 4 * i), mv[c]);
+            for (int c = 0; c < 3; ++c) widen4(nx[c], mv[c]);
+            if (i + 32 < it.n4) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * (i + 32));
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const double n = sqrt((mv[0][j] * mv[0][j] + mv[1][j] * mv[1][j]) + mv[2][j] * mv[2][j]);
@@ -632,11 +642,20 @@ llg_norm_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ Ma
         const unsigned char* pm = p.has_u ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)it.b * p.mask_u.sb + base : nullptr;
         float* gm = g_x0 + ((int64_t)it.b * p.C + p.ch_a) * plane + base;
         float* gd = g_dxdt ? g_dxdt + ((int64_t)it.b * p.C + p.ch_a) * plane + base : nullptr;
-#pragma unroll 2
+        float4 nx[3];
+        if (lane < it.n4) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * lane);
+        }
+#pragma unroll 1
         for (int i = lane; i < it.n4; i += 32) {
             double mv[3][4], f[4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) widen4(ldg4(m0 + c * p.x0.sc + 4 * i), mv[c]);
+            for (int c = 0; c < 3; ++c) widen4(nx[c], mv[c]);
+            if (i + 32 < it.n4) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * (i + 32));
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 // g_m = -c_p (1 - n) m / n  (0 where n == 0, as torch.linalg.norm's backward)
