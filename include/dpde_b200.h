@@ -83,13 +83,15 @@ int dpde_abi_version(void);
 const char* dpde_last_error(void);
 
 /* Kernel selection: 1 (default) lets eligible problems (fp32 fields, W % 4 == 0, 16-byte aligned operands, fp32
-   observations, uint8 masks) take the register row-marching kernels; 0 forces the generic tile kernels, which accept
-   every layout.  Both give the same results (tests run both).  Returns the previous setting. */
+   observations, uint8 masks) take the fast paths -- register row-marching kernels for the heat residual, convert-once
+   shared-memory tiles for the LLG m x H_eff residual, 128-bit streaming for the soft-norm loss; 0 forces the generic
+   tile kernels, which accept every layout.  Both give the same results (tests run both).  Returns the previous setting. */
 int dpde_set_fast_path(int enable);
 
 /* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 = 120
-   columns + 1 halo lane; 1 = 112 + 2, sector aligned), key 1 = 1 disables the warp-uniform kernels, key 2 rows per
-   chunk (0 = automatic), key 3 = 1 keeps a-planes as separate streaming items.  Process-wide, not thread-safe. */
+   columns + 1 halo lane; 1 (default) = 112 + 2, sector aligned), key 2 rows per chunk (0 = automatic: up to 128 in the
+   VJP, 64 in the reduce pass), keys 3 / 4 = 1 pair every a-plane with the u-plane of the same index in the reduce /
+   VJP pass instead of streaming it as separate work items.  Process-wide, not thread-safe. */
 int dpde_set_tuning(int key, int value);
 
 /* Bytes of scratch the reduce pass needs (per-CTA partial sums + a ticket counter).  The caller zero-fills it
