@@ -619,7 +619,7 @@ MarchGeom march_geometry(const Params& p, bool vjp) {
     // measured on 8x2x4096^2, VJP 4.41 / 4.53 / 4.73 TB/s at R = 32 / 64 / 128, reduce best at 64), short ones expose
     // more warps on small problems: take the longest chunk that still leaves two items per resident warp.
     const int64_t per_row_items = (int64_t)g.strips * p.n_u_units * p.B;
-    const int64_t want_warps = (int64_t)sm_count() * 16;
+    const int64_t want_warps = (int64_t)sm_count() * (vjp ? 16 : 24);
     int R = vjp ? 128 : 64;
     while (R > 32 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < 2 * want_warps) R >>= 1;
     while (R > 4 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
@@ -663,7 +663,7 @@ int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
 template <bool HAS_D, bool HAS_O, int PA>
 int launch_march_reduce_pa(const Params& p, const MarchGeom& g, double* partials, unsigned int* ticket, double* sums, int finalize,
                            double* scal, float* trace, cudaStream_t s) {
-    constexpr int smem = ring_bytes(PA);
+    constexpr int smem = ring_bytes(PA, false);
     auto k = heat_march_reduce_kernel<HAS_D, HAS_O, PA>;
     k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
     return check_launch("dpde_guidance_reduce (march)");
@@ -683,7 +683,7 @@ int launch_march_reduce(const Params& p, double* partials, unsigned int* ticket,
 template <bool HAS_D, bool HAS_O, int PA>
 int launch_march_vjp_pa(const Params& p, const MarchGeom& g, const double* scal, const double* upstream, float* g_x0,
                         float* g_dxdt, cudaStream_t s) {
-    constexpr int smem = ring_bytes(PA);
+    constexpr int smem = ring_bytes(PA, true);
     auto k = heat_march_vjp_kernel<HAS_D, HAS_O, PA>;
     k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
     return check_launch("dpde_guidance_vjp (march)");

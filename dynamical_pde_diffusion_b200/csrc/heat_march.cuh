@@ -44,8 +44,10 @@ __device__ __forceinline__ uchar4 ldg4(const unsigned char* p) { return __ldg(re
 // streaming work items (8-deep ring of u / dudt / obs_u / mask_u: 106496 B);  PA = 1 / 2: every marching item also
 // carries the a-plane of the same index (requires ch_a == number of u-planes), whose row, observation and mask
 // (PA == 1; PA == 2: mask_a empty, nothing to read, ring as PA = 0) ride in the same ring element -- 4 deep, 90112 B.
-__host__ __device__ constexpr int ring_depth(int PA) { return PA == 1 ? 4 : 8; }
-__host__ __device__ constexpr int ring_bytes(int PA) { return ring_depth(PA) * kThreads * (PA == 1 ? 5 * 16 + 2 * 4 : 3 * 16 + 4); }
+// The reduce pass carries no residual window and no output pointers: it fits 80 registers, so with a 4-deep ring
+// (53 KB) THREE CTAs share an SM (24 warps instead of 16) -- it is issue-bound, not bandwidth-bound.
+__host__ __device__ constexpr int ring_depth(int PA, bool vjp) { return (PA == 1 || !vjp) ? 4 : 8; }
+__host__ __device__ constexpr int ring_bytes(int PA, bool vjp) { return ring_depth(PA, vjp) * kThreads * (PA == 1 ? 5 * 16 + 2 * 4 : 3 * 16 + 4); }
 
 // shared-memory operands are 32-bit shared-window addresses computed once per thread (the generic->shared
 // conversion otherwise costs ~6 instructions per copy)
@@ -115,9 +117,9 @@ __device__ __forceinline__ int row_offset(const Params& p, int y) {
 
 // Per-lane prefetch ring.  Element s holds u, dudt, obs and mask (and, paired, a / obs_a / mask_a) of row (row0 + s)
 // for the lane's four columns.  HAS_D / HAS_O / PA are compile-time, so the loop carries no pointer tests.
-template <bool HAS_D, bool HAS_O, int PA>
+template <bool HAS_D, bool HAS_O, int PA, bool VJP>
 struct RowRing {
-    static constexpr int RD = ring_depth(PA);
+    static constexpr int RD = ring_depth(PA, VJP);
     unsigned su, sd, so, sm, sa, soa, sma;   // shared-window byte addresses of this lane's slot 0 in each field ring
     const float *u, *du, *ob, *a, *oa;
     const unsigned char *mk, *ma;
@@ -232,7 +234,7 @@ __device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, 
 // pass 1 (fast): S_a, S_u, S_pde
 // ---------------------------------------------------------------------------------------------------------
 template <bool HAS_D, bool HAS_O, int PA>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g,
                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
                          int finalize, double* __restrict__ scal, float* __restrict__ trace) {
@@ -265,8 +267,8 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     // ---- u-planes: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1].
     //      Ring element s is row ys + s:  uc comes from element it+1, dudt / obs / mask from element it.
     const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O, PA> ring;
-    constexpr int kRing = ring_depth(PA);
+    RowRing<HAS_D, HAS_O, PA, false> ring;
+    constexpr int kRing = ring_depth(PA, false);
     ring.init(ring_mem, tid);
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
@@ -397,8 +399,8 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
     //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
     const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O, PA> ring;
-    constexpr int kRing = ring_depth(PA);
+    RowRing<HAS_D, HAS_O, PA, true> ring;
+    constexpr int kRing = ring_depth(PA, true);
     ring.init(ring_mem, tid);
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);

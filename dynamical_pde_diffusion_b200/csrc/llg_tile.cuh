@@ -573,7 +573,7 @@ __device__ __forceinline__ void widen4(const float4& f, double* d) {
     d[0] = (double)f.x; d[1] = (double)f.y; d[2] = (double)f.z; d[3] = (double)f.w;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)   // measured 8x6x2048^2: 0.277 / 0.215 / 0.233 ms at 2 / 3 / 4 CTAs per SM
 llg_norm_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, int n_items,
                        double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
                        int finalize, double* __restrict__ scal, float* __restrict__ trace) {
@@ -625,7 +625,7 @@ llg_norm_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__
     reduce_epilogue(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)   // measured 8x6x2048^2: 0.547 / 0.458 / 0.400 ms at 2 / 3 / 4 CTAs per SM
 llg_norm_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, int n_items,
                     const double* __restrict__ scal, const double* __restrict__ upstream, float* __restrict__ g_x0,
                     float* __restrict__ g_dxdt) {
