@@ -572,10 +572,11 @@ laplacian_kernel(const T* __restrict__ u, T* __restrict__ out, int64_t planes, i
 // host side
 // =========================================================================================================
 bool g_fast_path = true;
-// experiment knobs (dpde_set_tuning): [0] strip layout 0 = 120 columns + 1 halo lane, 1 = 112 + 2 (sector aligned);
+// experiment knobs (dpde_set_tuning): [0] strip layout 0 = per pass (reduce 120 columns + 1 halo lane, VJP 112 + 2,
+// sector aligned), 1 = 120 + 1 in both, 2 = 112 + 2 in both;
 // [1] unused; [2] rows per chunk (0 = automatic); [3] / [4] 1 = pair a-planes with u-planes in the
 // reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s)
-int g_tuning[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
@@ -612,7 +613,11 @@ MarchGeom march_geometry(const Params& p, bool vjp) {
         g.lw_log2 = l2; g.segs_per_warp = 32 / lw; g.strips = 1; g.strip_w = p.W; g.halo_lane = 0;
     } else {
         g.lw_log2 = 5; g.segs_per_warp = 1;
-        if (g_tuning[0] == 0) { g.strip_w = 120; g.halo_lane = 1; } else { g.strip_w = 112; g.halo_lane = 2; }
+        // strip layout per pass (measured, 8x2x4096^2): the reduce pass needs one halo column and is issue-bound, so the
+        // 120 + 1 layout (6 % idle lanes) beats the sector-aligned 112 + 2 (12.5 %): 4.48 vs 4.11 TB/s; the VJP needs two
+        // halo columns and is closer to the memory system's limits: 4.75 (112 + 2) vs 4.59 TB/s (120 + 1)
+        const bool narrow_halo = g_tuning[0] == 0 ? !vjp : g_tuning[0] == 1;
+        if (narrow_halo) { g.strip_w = 120; g.halo_lane = 1; } else { g.strip_w = 112; g.halo_lane = 2; }
         g.strips = (p.W + g.strip_w - 1) / g.strip_w;
     }
     // rows per chunk: long chunks amortise the warm-up rows (2 of R + 2 in the reduce pass, 4 of R + 4 in the VJP:

@@ -88,8 +88,8 @@ const char* dpde_last_error(void);
    tile kernels, which accept every layout.  Both give the same results (tests run both).  Returns the previous setting. */
 int dpde_set_fast_path(int enable);
 
-/* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 = 120
-   columns + 1 halo lane; 1 (default) = 112 + 2, sector aligned), key 2 rows per chunk (0 = automatic: up to 128 in the
+/* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 (default) =
+   per pass: 120 columns + 1 halo lane in the reduce pass, 112 + 2 sector aligned in the VJP; 1 / 2 force one of them), key 2 rows per chunk (0 = automatic: up to 128 in the
    VJP, 64 in the reduce pass), keys 3 / 4 = 1 pair every a-plane with the u-plane of the same index in the reduce /
    VJP pass instead of streaming it as separate work items.  Process-wide, not thread-safe. */
 int dpde_set_tuning(int key, int value);
