@@ -233,6 +233,8 @@ def run_ours(args):
     if args.channels_last:                                         # PyTorch-level layout choice for the denoiser only
         net = net.to(memory_format=torch.channels_last)
     loss_fn, loss_kwargs, provider = pde_plugins(pde, True, prob["dx"])
+    if args.fd_batched:                                            # opt-in: the two offset evaluations as one 2B-batch call
+        provider = dp.X_and_dXdt_fd_batched
     smp = dp.JointSampler(net, dev, (H, W), C_, B, ch_a, loss_fn, loss_kwargs, num_steps=n_cfg, out_and_grad_fn=provider)
     z = (prob["zeta_a"], prob["zeta_u"], prob["zeta_pde"])
     host = {k: prob[k].pin_memory() for k in ("labels", "obs_a", "obs_u", "mask_a", "mask_u")}
@@ -407,6 +409,7 @@ def main():
     ap.add_argument("--e2e-budget", type=float, default=45.0, help="seconds the end-to-end sample() call may take")
     ap.add_argument("--ieee", action="store_true", help="IEEE fp32 convolutions instead of the reference's TF32 setting")
     ap.add_argument("--channels-last", action="store_true", help="run the PyTorch denoiser in NHWC memory format")
+    ap.add_argument("--fd-batched", action="store_true", help="finite-difference offsets as one denoiser call of batch 2B")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-large", action="store_true")

@@ -3,7 +3,7 @@
 Importing the package does not need a GPU; calling any op does (there is no CPU fallback).
 """
 from .ops import GuidanceEngine, LLGConstants, heat_loss2, laplacian, llg_loss2, llg_residual_loss  # noqa: F401
-from .sampler import JointSampler, Sampler, UnconditionalSampler, X_and_dXdt, X_and_dXdt_dummy, X_and_dXdt_fd  # noqa: F401
+from .sampler import JointSampler, Sampler, UnconditionalSampler, X_and_dXdt, X_and_dXdt_dummy, X_and_dXdt_fd, X_and_dXdt_fd_batched  # noqa: F401
 
 __all__ = ["GuidanceEngine", "LLGConstants", "heat_loss2", "laplacian", "llg_loss2", "llg_residual_loss",
-           "JointSampler", "Sampler", "UnconditionalSampler", "X_and_dXdt", "X_and_dXdt_dummy", "X_and_dXdt_fd"]
+           "JointSampler", "Sampler", "UnconditionalSampler", "X_and_dXdt", "X_and_dXdt_dummy", "X_and_dXdt_fd", "X_and_dXdt_fd_batched"]

@@ -51,6 +51,24 @@ def X_and_dXdt_fd(net, x, sigma, labels, eps=1e-5, no_grad=True, **kwargs):
     return net(x, sigma, labels, **kwargs), dudt
 
 
+def X_and_dXdt_fd_batched(net, x, sigma, labels, eps=1e-5, **kwargs):
+    """``X_and_dXdt_fd`` with the two offset evaluations batched into ONE denoiser call of batch 2B: two
+    thirds of the finite-difference launches disappear.  Per-sample arithmetic is unchanged, but a batch of 2B may make
+    cuDNN pick other kernels, and the difference quotient amplifies their 1e-7 differences by 1/(2 eps) -- so this is an
+    opt-in provider, not the parity default."""
+    if labels is None:
+        return X_and_dXdt_dummy(net, x, sigma, labels, **kwargs)
+    with torch.no_grad():
+        lbl = labels.detach().repeat(2, 1)
+        lbl[: labels.shape[0], 0] += eps
+        lbl[labels.shape[0]:, 0] -= eps
+        xd = x.detach()
+        out = net(torch.cat([xd, xd]), torch.cat([sigma, sigma]), lbl, **kwargs)
+        up, um = out[: labels.shape[0]], out[labels.shape[0]:]
+        dudt = torch.sub(up, um).div_(2 * eps)
+    return net(x, sigma, labels, **kwargs), dudt
+
+
 def X_and_dXdt(net, x, sigma, labels):
     """Exact time derivative by forward-mode AD in ``labels[:, 0]`` (``sample.py:69-103``)."""
     t0 = labels[:, 0]

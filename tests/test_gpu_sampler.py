@@ -238,6 +238,21 @@ def test_run_sweep_equals_direct_calls():
             np.testing.assert_allclose(final[zi, si], np.mean(rows, axis=0), rtol=1e-6)
 
 
+def test_batched_fd_provider_matches_the_unbatched_one():
+    import dynamical_pde_diffusion_b200 as dp
+
+    gold = load_golden("joint_heat.npz")
+    net = net_from_golden(gold, 2, 2, device=_dev())
+    x = torch.from_numpy(gold["net_in"]).to(_dev()).requires_grad_()
+    sig, lab = torch.from_numpy(gold["net_sigma"]).to(_dev()), torch.from_numpy(gold["labels"]).to(_dev())
+    x0a, da = dp.X_and_dXdt_fd(net, x, sig, lab)
+    x0b, db = dp.X_and_dXdt_fd_batched(net, x, sig, lab)
+    assert torch.equal(x0a, x0b) and x0b.requires_grad and not db.requires_grad
+    # the quotient amplifies kernel-selection differences (batch B vs 2B) by 1/(2 eps) = 5e4: compare at that scale
+    scale = float(x0a.abs().max()) * 1.2e-7 / 2e-5
+    assert float((da - db).abs().max()) <= 8 * scale, (float((da - db).abs().max()), scale)
+
+
 def test_sampler_refuses_cpu():
     import dynamical_pde_diffusion_b200 as dp
 
