@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python __graft_entry__.py smoke 2>&1 | tail -2
-bash scripts/profile_round.sh r1k > gpurun_out/r1k_profile_round.log 2>&1; tail -5 gpurun_out/r1k_profile_round.log
+python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "llg or slab or tuning" 2>&1 | tail -3
+python scripts/kernel_probe.py 8 2048 2048 --llg
+scripts/ncu_times.sh 32 128 128 --llg

@@ -175,6 +175,34 @@ def test_heat_guidance_matches_closed_form(shape, mask_mode, kernel_path):
     assert torch.all(gd[:, :ch_a] == 0)
 
 
+@pytest.mark.parametrize("tune", [{0: 1}, {0: 2}, {2: 8}, {2: 128}, {3: 1}, {4: 1}, {3: 1, 4: 1, 0: 2}])
+def test_tuning_knobs_never_change_results(tune):
+    """dpde_set_tuning selects strip layouts / chunk lengths / a-plane pairing of the marching kernels: speed only."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_HEAT
+
+    dev, w = _dev(), (20.0, 0.5, 20.0)
+    for (B, ch_a, cu, H, W) in [(2, 1, 1, 70, 260), (3, 1, 1, 33, 128), (1, 2, 2, 40, 520)]:
+        x0, dxdt, labels, obs_a, obs_u, mask_a, mask_u = _heat_case(B, ch_a, cu, H, W, seed=H + W)
+        def run():
+            eng = GuidanceEngine(B, ch_a + cu, ch_a, H, W, PDE_HEAT, dev, obs_a=obs_a.to(dev), mask_a=mask_a.to(dev), obs_u=obs_u.to(dev),
+                                 mask_u=mask_u.to(dev), sample_coef=labels[:, -1].double().to(dev), dx=1.0 / (H - 1))
+            g, gd = eng.seed(x0.to(dev), dxdt.to(dev), w, want_dxdt_grad=True)
+            return eng.scalars[:4].clone(), g, gd
+        s0, g0, gd0 = run()
+        try:
+            for k, v in tune.items():
+                _ffi.check(_ffi.lib().dpde_set_tuning(k, v))
+            s1, g1, gd1 = run()
+        finally:
+            for k in tune:
+                _ffi.check(_ffi.lib().dpde_set_tuning(k, 0))
+        _close(s1, s0, 1e-13, "losses under tuning")          # partial sums are grouped differently: summation order only
+        _close(g1, g0, 2e-7, "seed under tuning")
+        _close(gd1, gd0, 2e-7, "d/d dudt under tuning")
+    assert _ffi.lib().dpde_set_tuning(99, 0) != 0
+
+
 def test_heat_guidance_fp64_fields_and_autograd_cross_check():
     """fp64 fields (what the unmodified sampler holds) and an independent check against torch autograd on the device."""
     from dynamical_pde_diffusion_b200 import GuidanceEngine
