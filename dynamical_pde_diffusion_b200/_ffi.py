@@ -22,7 +22,8 @@ EXPORTED = (
     "dpde_guidance_finalize", "dpde_guidance_vjp", "dpde_laplacian", "dpde_sampler_init", "dpde_euler_predict",
     "dpde_euler_predict_bwd", "dpde_heun_guided_update", "dpde_heun_guided_update_rows", "dpde_halo_pack", "dpde_halo_unpack",
     "dpde_set_fast_path", "dpde_peer_alloc", "dpde_peer_free", "dpde_peer_export", "dpde_peer_open", "dpde_peer_close",
-    "dpde_halo_push", "dpde_flag_wait", "dpde_set_tuning",
+    "dpde_halo_push", "dpde_flag_wait", "dpde_set_tuning", "dpde_heat_residual_sq_workspace_bytes", "dpde_heat_residual_sq",
+    "dpde_heat_residual_sq_vjp",
 )
 
 
@@ -83,9 +84,14 @@ def lib():
     L.dpde_halo_unpack.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.dpde_set_fast_path.argtypes = [C.c_int]
     L.dpde_set_tuning.argtypes = [C.c_int, C.c_int]
+    L.dpde_heat_residual_sq_workspace_bytes.argtypes = [i32]
+    L.dpde_heat_residual_sq_workspace_bytes.restype = C.c_size_t
+    L.dpde_heat_residual_sq.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp, dbl, vp, vp, vp]
+    L.dpde_heat_residual_sq_vjp.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp, dbl, vp, vp, vp, vp]
     for name in EXPORTED:
         fn = getattr(L, name)
-        if name not in ("dpde_abi_version", "dpde_last_error", "dpde_guidance_workspace_bytes"):
+        if name not in ("dpde_abi_version", "dpde_last_error", "dpde_guidance_workspace_bytes",
+                        "dpde_heat_residual_sq_workspace_bytes"):
             fn.restype = C.c_int
     _lib = L
     return L

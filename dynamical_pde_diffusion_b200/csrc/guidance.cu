@@ -565,6 +565,72 @@ laplacian_kernel(const T* __restrict__ u, T* __restrict__ out, int64_t planes, i
     }
 }
 
+// =========================================================================================================
+// per-sample heat residual of the training-time physics loss (EDMHeatLoss, models/loss.py:143):
+//   out[b] = sum_{c,h,w} (dudt - alpha_b lap(u))^2          (the caller applies 1/(H W), mean / sum and coeff / sigma^2)
+// and its VJP   g_u = up_b 2 (-alpha_b / dx^2) K^T r,   g_dudt = up_b 2 r.
+// Two-level deterministic reduction: kPerSampleBlocks partial sums per sample, combined in index order.
+// =========================================================================================================
+constexpr int kPerSampleBlocks = 1024;   // upper bound on partial sums per sample (workspace = B x this)
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+heat_residual_sq_kernel(const T* __restrict__ u, const T* __restrict__ dudt, int64_t sb_u, int64_t sc_u, int64_t sb_d, int64_t sc_d,
+                        const double* __restrict__ alpha, int Cu, int H, int W, double inv_dx2, double* __restrict__ partials) {
+    __shared__ double scratch[3 * (kThreads / 32)];
+    const int b = blockIdx.y, hw = H * W;
+    const int64_t total = (int64_t)Cu * hw;
+    const double a_s = __ldg(alpha + b) * inv_dx2;
+    double acc = 0.0, z0 = 0.0, z1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int c = (int)(i / hw), r = (int)(i - (int64_t)c * hw), y = r / W, x = r - y * W;
+        double centre;
+        const double s = lap5(u + b * sb_u + c * sc_u, y, x, y, H, W, centre);
+        const double dt = dudt ? ldg_d(dudt + b * sb_d + c * sc_d + r) : 0.0;
+        const double res = dt - a_s * s;
+        acc += res * res;
+    }
+    block_sum3(acc, z0, z1, scratch);
+    if (threadIdx.x == 0) partials[(int64_t)b * gridDim.x + blockIdx.x] = acc;
+}
+
+__global__ void per_sample_combine_kernel(const double* __restrict__ partials, int nblk, int B, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int k = 0; k < nblk; ++k) s += partials[(int64_t)b * nblk + k];
+    out[b] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+heat_residual_sq_vjp_kernel(const T* __restrict__ u, const T* __restrict__ dudt, int64_t sb_u, int64_t sc_u, int64_t sb_d, int64_t sc_d,
+                            const double* __restrict__ alpha, const double* __restrict__ upstream, int B, int Cu, int H, int W,
+                            double inv_dx2, T* __restrict__ g_u, T* __restrict__ g_dudt) {
+    const int hw = H * W;
+    const int64_t total = (int64_t)B * Cu * hw;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t pl = i / hw;
+        const int b = (int)(pl / Cu), c = (int)(pl - (int64_t)b * Cu), r = (int)(i - pl * hw), y = r / W, x = r - y * W;
+        const T* up = u + b * sb_u + c * sc_u;
+        const T* dp = dudt ? dudt + b * sb_d + c * sc_d : nullptr;
+        const double a_s = __ldg(alpha + b) * inv_dx2, seed = 2.0 * __ldg(upstream + b);
+        auto res = [&](int yy, int xx) {
+            double centre;
+            const double s = lap5(up, yy, xx, yy, H, W, centre);
+            return (dp ? ldg_d(dp + (int64_t)yy * W + xx) : 0.0) - a_s * s;
+        };
+        const double rc = res(y, x);
+        double acc = -4.0 * rc;
+        if (y > 0) acc += adj_w(y - 1, H) * res(y - 1, x);
+        if (y < H - 1) acc += adj_w(y + 1, H) * res(y + 1, x);
+        if (x > 0) acc += adj_w(x - 1, W) * res(y, x - 1);
+        if (x < W - 1) acc += adj_w(x + 1, W) * res(y, x + 1);
+        g_u[i] = (T)(seed * (-a_s) * acc);
+        if (g_dudt) g_dudt[i] = (T)(seed * rc);
+    }
+}
+
 #include "heat_march.cuh"
 #include "llg_tile.cuh"
 
@@ -1006,6 +1072,52 @@ int dpde_laplacian(const void* u, void* out, int32_t dtype, int64_t planes, int3
     else
         laplacian_kernel<double><<<(int)blocks, kThreads, 0, s>>>((const double*)u, (double*)out, planes, H, W, plane_stride_in, inv, adjoint);
     return check_launch("dpde_laplacian");
+}
+
+size_t dpde_heat_residual_sq_workspace_bytes(int32_t B) { return (size_t)(B > 0 ? B : 0) * kPerSampleBlocks * sizeof(double); }
+
+int dpde_heat_residual_sq(const void* u, const void* dudt, int32_t dtype, int32_t B, int32_t Cu, int32_t H, int32_t W, int64_t sb_u,
+                          int64_t sc_u, int64_t sb_d, int64_t sc_d, const double* alpha, double dx, void* workspace, double* out,
+                          dpde_stream_t stream) {
+    if (!u || !alpha || !workspace || !out) return fail(DPDE_ERR_INVALID, "dpde_heat_residual_sq: null pointer");
+    if (B < 0 || Cu < 1 || H < 2 || W < 2) return fail(DPDE_ERR_INVALID, "dpde_heat_residual_sq: need B >= 0, Cu >= 1, H, W >= 2");
+    if (!(dx > 0.0)) return fail(DPDE_ERR_INVALID, "dpde_heat_residual_sq: dx must be > 0");
+    if (dtype != DPDE_F32 && dtype != DPDE_F64) return fail(DPDE_ERR_UNSUPPORTED, "dpde_heat_residual_sq: dtype must be f32/f64");
+    if (B == 0) return DPDE_OK;
+    if (B > 65535) return fail(DPDE_ERR_UNSUPPORTED, "dpde_heat_residual_sq: at most 65535 samples per call");
+    const double inv = 1.0 / (dx * dx);
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t nblk = ((int64_t)Cu * H * W + 8 * kThreads - 1) / (8 * kThreads);   // ~8 pixels per thread
+    if (nblk > kPerSampleBlocks) nblk = kPerSampleBlocks;
+    const dim3 grid((unsigned)nblk, (unsigned)B);
+    double* partials = reinterpret_cast<double*>(workspace);
+    if (dtype == DPDE_F32)
+        heat_residual_sq_kernel<float><<<grid, kThreads, 0, s>>>((const float*)u, (const float*)dudt, sb_u, sc_u, sb_d, sc_d, alpha, Cu, H, W, inv, partials);
+    else
+        heat_residual_sq_kernel<double><<<grid, kThreads, 0, s>>>((const double*)u, (const double*)dudt, sb_u, sc_u, sb_d, sc_d, alpha, Cu, H, W, inv, partials);
+    per_sample_combine_kernel<<<(B + 127) / 128, 128, 0, s>>>(partials, (int)nblk, B, out);
+    return check_launch("dpde_heat_residual_sq");
+}
+
+int dpde_heat_residual_sq_vjp(const void* u, const void* dudt, int32_t dtype, int32_t B, int32_t Cu, int32_t H, int32_t W, int64_t sb_u,
+                              int64_t sc_u, int64_t sb_d, int64_t sc_d, const double* alpha, double dx, const double* upstream,
+                              void* g_u, void* g_dudt, dpde_stream_t stream) {
+    if (!u || !alpha || !upstream || !g_u) return fail(DPDE_ERR_INVALID, "dpde_heat_residual_sq_vjp: null pointer");
+    if (B < 0 || Cu < 1 || H < 2 || W < 2) return fail(DPDE_ERR_INVALID, "dpde_heat_residual_sq_vjp: need B >= 0, Cu >= 1, H, W >= 2");
+    if (!(dx > 0.0)) return fail(DPDE_ERR_INVALID, "dpde_heat_residual_sq_vjp: dx must be > 0");
+    if (dtype != DPDE_F32 && dtype != DPDE_F64) return fail(DPDE_ERR_UNSUPPORTED, "dpde_heat_residual_sq_vjp: dtype must be f32/f64");
+    if (B == 0) return DPDE_OK;
+    const int64_t total = (int64_t)B * Cu * H * W;
+    int64_t blocks = (total + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const double inv = 1.0 / (dx * dx);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == DPDE_F32)
+        heat_residual_sq_vjp_kernel<float><<<(int)blocks, kThreads, 0, s>>>((const float*)u, (const float*)dudt, sb_u, sc_u, sb_d, sc_d, alpha, upstream, B, Cu, H, W, inv, (float*)g_u, (float*)g_dudt);
+    else
+        heat_residual_sq_vjp_kernel<double><<<(int)blocks, kThreads, 0, s>>>((const double*)u, (const double*)dudt, sb_u, sc_u, sb_d, sc_d, alpha, upstream, B, Cu, H, W, inv, (double*)g_u, (double*)g_dudt);
+    return check_launch("dpde_heat_residual_sq_vjp");
 }
 
 }  // extern "C"

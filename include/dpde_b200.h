@@ -120,6 +120,23 @@ int dpde_guidance_vjp(const dpde_guidance_desc* desc, const double* scalars, con
 int dpde_laplacian(const void* u, void* out, int32_t dtype, int64_t planes, int32_t H, int32_t W,
                    int64_t plane_stride_in, double dx, int32_t adjoint, dpde_stream_t stream);
 
+/* ---- Training-time physics loss (next row f-2): EDMHeatLoss, models/loss.py:143 ------------------------------------
+   out[b] = sum_{c,h,w} (dudt - alpha_b laplacian(u, dx))^2  for u, dudt (B, Cu, H, W) with rows contiguous and free
+   batch / channel strides (x_0star[:, ch_a:] is a channel-slice view), alpha_b = labels[b, 1].  The caller applies
+   1/(H W), the mean / sum over (C, H, W) and pde_loss_coeff / sigma^2 (models/loss.py:143-149) with torch ops.
+   `workspace`: dpde_heat_residual_sq_workspace_bytes(B) bytes of device scratch.  dudt == NULL means zeros. */
+size_t dpde_heat_residual_sq_workspace_bytes(int32_t B);
+int dpde_heat_residual_sq(const void* u, const void* dudt, int32_t dtype, int32_t B, int32_t Cu, int32_t H, int32_t W,
+                          int64_t stride_b_u, int64_t stride_c_u, int64_t stride_b_dudt, int64_t stride_c_dudt,
+                          const double* alpha, double dx, void* workspace, double* out, dpde_stream_t stream);
+
+/* Its VJP: g_u (B,Cu,H,W contiguous, dtype of u) = upstream_b * 2 * (-alpha_b/dx^2) K^T r, g_dudt (may be NULL) =
+   upstream_b * 2 * r, with r = dudt - alpha_b laplacian(u) and K^T the transposed reflect-padded stencil. */
+int dpde_heat_residual_sq_vjp(const void* u, const void* dudt, int32_t dtype, int32_t B, int32_t Cu, int32_t H, int32_t W,
+                              int64_t stride_b_u, int64_t stride_c_u, int64_t stride_b_dudt, int64_t stride_c_dudt,
+                              const double* alpha, double dx, const double* upstream, void* g_u, void* g_dudt,
+                              dpde_stream_t stream);
+
 /* x = latents * sigma_0 (sample.py:316); also emits the fp32 copy the denoiser reads (sample.py:324). */
 int dpde_sampler_init(const double* latents, double sigma0, double* x64, float* x32, int64_t n, dpde_stream_t stream);
 

@@ -302,6 +302,41 @@ def unconditional_sample(net, device, sample_shape, num_channels, labels=None, n
     return x_next.to(F32).detach().cpu()
 
 
+def edm_heat_loss(net, x, labels, dx, noise, pde_loss_coeff=1.0, method="joint", residual_estimation="ME", P_mean=-1.2,
+                  P_std=1.2, sigma_data=0.5, reduce_method="mean", sigma_min=0.01, rho=7.0, steps=2):
+    """Restatement of EDMHeatLoss.__call__ (models/loss.py:127-171) with the two torch.randn draws (loss.py:129,132)
+    passed in as ``noise = (rnd_normal, eps)``.  Same dtype as the reference: the Laplacian is an fp32 conv2d."""
+    ch_a = 1 if method == "joint" else 0
+    rnd_normal, eps = noise
+    sigma = (rnd_normal * P_std + P_mean).exp()
+    weight = (sigma ** 2 + sigma_data ** 2) / (sigma * sigma_data) ** 2
+    n = eps * sigma
+    D_yn, dxdt = X_and_dXdt_fd(net, x + n, sigma.flatten(), labels, no_grad=False)
+    dxdt = dxdt.detach()[:, ch_a:, ...]
+    edm_loss = weight * ((D_yn - x) ** 2)
+    if residual_estimation == "ME":
+        x_0star = D_yn
+    else:   # two_step_sample, loss.py:78-124
+        B = x.shape[0]
+        s_max = sigma.view(B)
+        s_min = torch.tensor(float(sigma_min), device=x.device, dtype=torch.float32)
+        idx = torch.arange(steps + 1, dtype=torch.float32, device=x.device)
+        sig = torch.stack([(s_max[i] ** (1.0 / rho) + idx / steps * (s_min ** (1.0 / rho) - s_max[i] ** (1.0 / rho))) ** rho
+                           for i in range(B)], dim=0)
+        x_0star = D_yn
+        for s_cur, s_next in zip(sig.T[:-1], sig.T[1:]):
+            x_N = net(x_0star, s_cur.flatten(), labels)
+            x_0star = x_0star + (s_next.view(B, 1, 1, 1) - s_cur.view(B, 1, 1, 1)) * ((x_0star - x_N) / s_cur.view(B, 1, 1, 1))
+    pde_loss = (dxdt - labels[:, 1].view(-1, 1, 1, 1) * laplacian(x_0star[:, ch_a:, ...], dx)) ** 2 / (x.shape[-2] * x.shape[-1])
+    if reduce_method == "mean":
+        edm_loss = edm_loss.mean(dim=(1, 2, 3))
+        pde_loss = pde_loss.mean(dim=(1, 2, 3)) * pde_loss_coeff / (sigma ** 2)
+    else:
+        edm_loss = edm_loss.sum(dim=(1, 2, 3))
+        pde_loss = pde_loss.sum(dim=(1, 2, 3)) * pde_loss_coeff / (sigma ** 2)
+    return edm_loss + pde_loss
+
+
 # ----------------------------------------------------------------------------------------
 # closed-form seed gradients (numpy, fp64) -- what the CUDA VJP kernels implement
 # ----------------------------------------------------------------------------------------

@@ -157,16 +157,47 @@ def golden_unconditional(S, M):
                         num_steps=np.int64(N))
 
 
+def golden_edm_heat_loss(M):
+    """EDMHeatLoss.__call__ (models/loss.py:127-171) with the denoiser of joint_heat.npz; the two internal torch.randn
+    draws are reproduced from the same seed and stored, so a test can feed them back (``noise=``)."""
+    torch.use_deterministic_algorithms(True)
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(23)
+    H, W, B = 16, 12, 3
+    net = _tiny_net(M, 2, 2, seed=21)
+    x = torch.randn(B, 2, H, W, generator=g)
+    labels = torch.stack([0.5 * torch.rand(B, generator=g), torch.exp(-2.5 + 3 * torch.rand(B, generator=g))], 1).float()
+    dx = 1.0 / (H - 1)
+    out = {"x": _np(x), "labels": _np(labels), "dx": np.float64(dx)}
+    w0 = next(p for p in net.parameters() if p.ndim == 4)
+    for tag, kw in (("me_mean", dict(residual_estimation="ME", reduce_method="mean")),
+                    ("me_sum", dict(residual_estimation="ME", reduce_method="sum")),
+                    ("se_mean", dict(residual_estimation="SE", reduce_method="mean"))):
+        seed = 40 + len(tag)
+        torch.manual_seed(seed)
+        rnd = torch.randn([B, 1, 1, 1])
+        eps = torch.randn_like(x)
+        torch.manual_seed(seed)
+        loss = M.EDMHeatLoss(dx, pde_loss_coeff=0.37, **kw)(net, x, labels)
+        (gw,) = torch.autograd.grad(loss.mean(), [w0])
+        out.update({f"{tag}_rnd": _np(rnd), f"{tag}_eps": _np(eps), f"{tag}_loss": _np(loss), f"{tag}_gw0": _np(gw)})
+    np.savez_compressed(os.path.join(OUT, "edm_heat_loss.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     S, PL, M = import_reference()
     if "--only-unconditional" in sys.argv:
         golden_unconditional(S, M)
         return
+    if "--only-edm-heat-loss" in sys.argv:
+        golden_edm_heat_loss(M)
+        return
     golden_laplacian(S)
     golden_pde_losses(PL)
     golden_joint(S, PL, M)
     golden_unconditional(S, M)
+    golden_edm_heat_loss(M)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -67,6 +67,22 @@ def timed(label, nbytes, fn):
     print(f"{label:34s} {ms:8.4f} ms  {nbytes / ms / 1e6:8.1f} GB/s (algorithmic)")
 
 
+if "--train" in sys.argv:                # per-sample residual of the training loss (models/loss.py:143), u / dudt (B,1,H,W)
+    from dynamical_pde_diffusion_b200 import training as T
+    u = x0[:, -1:].detach().requires_grad_()
+    d = dxdt[:, -1:].detach().requires_grad_()
+    alpha = torch.rand(B, device=dev)
+    px = B * H * W
+    hold = {}
+    def fwd():
+        hold["out"] = T.heat_residual_sq(u, d, alpha, 1.0 / (H - 1))
+    timed("heat_residual_sq", 8 * px, fwd)
+    up = torch.ones(B, device=dev)
+    def bwd():
+        hold["g"] = torch.autograd.grad(hold["out"], [u, d], grad_outputs=up, retain_graph=True)
+    timed("heat_residual_sq_vjp", 16 * px, bwd)
+    sys.exit(0)
+
 kinds = [("llg_residual", PDE_LLG_RESIDUAL), ("llg_norm", PDE_LLG_NORM)] if llg else [("heat", PDE_HEAT)]
 for name, kind in kinds:
     coef = None
