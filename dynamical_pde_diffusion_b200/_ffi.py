@@ -84,7 +84,7 @@ def lib():
     L.dpde_halo_unpack.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.dpde_set_fast_path.argtypes = [C.c_int]
     L.dpde_set_tuning.argtypes = [C.c_int, C.c_int]
-    L.dpde_heat_residual_sq_workspace_bytes.argtypes = [i32]
+    L.dpde_heat_residual_sq_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.dpde_heat_residual_sq_workspace_bytes.restype = C.c_size_t
     L.dpde_heat_residual_sq.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp, dbl, vp, vp, vp]
     L.dpde_heat_residual_sq_vjp.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp, dbl, vp, vp, vp, vp]

@@ -602,6 +602,17 @@ __global__ void per_sample_combine_kernel(const double* __restrict__ partials, i
     out[b] = s;
 }
 
+// marching path: partials[item], the items of sample b are b, b + B, ... (n_per of them).  One warp per sample: lane l
+// adds items l, l + 32, ... in order, then a fixed shuffle tree -- deterministic.
+__global__ void per_sample_items_kernel(const double* __restrict__ partials, int n_per, int B, double* __restrict__ out) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int k = lane; k < n_per; k += 32) s += partials[(int64_t)k * B + b];
+    s = warp_sum(s);
+    if (lane == 0) out[b] = s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 heat_residual_sq_vjp_kernel(const T* __restrict__ u, const T* __restrict__ dudt, int64_t sb_u, int64_t sc_u, int64_t sb_d, int64_t sc_d,
@@ -875,6 +886,44 @@ int launch_llg_vjp(const Params& p, const double* scal, const double* upstream, 
     }
 }
 
+// ---- per-sample heat residual (training loss) on the marching kernels ----------------------------------
+Params per_sample_params(const void* u, const void* dudt, int dtype, int B, int Cu, int H, int W, int64_t sb_u, int64_t sc_u,
+                         int64_t sb_d, int64_t sc_d, const double* alpha, double dx) {
+    Params p{};
+    p.B = B; p.C = Cu; p.ch_a = 0; p.H = H; p.W = W; p.kind = DPDE_PDE_HEAT; p.has_a = 0; p.has_u = 0;
+    p.Hg = H; p.yg0 = 0; p.ylo = 0; p.yhi = H; p.n_u_units = Cu; p.units_per_sample = Cu;
+    p.x0 = View{u, dtype, sb_u, sc_u};
+    p.dxdt = View{dudt, dtype, sb_d, sc_d};
+    p.coef = alpha;
+    p.inv_dx2 = 1.0 / (dx * dx);
+    p.hw = (double)H * (double)W;
+    return p;
+}
+
+// upper bound on the row-segment items of march_geometry for (B, Cu, H, W): chunks <= ceil(H/4), strips <= ceil(W/112)
+inline int64_t per_sample_item_bound(int B, int Cu, int H, int W) {
+    return (int64_t)B * Cu * ((H + 3) / 4) * (W <= 128 ? 1 : (W + 111) / 112);
+}
+
+template <bool HAS_D>
+int launch_march_per_sample_reduce(const Params& p, double* partials, double* out, cudaStream_t s) {
+    const MarchGeom g = march_geometry(p, false);
+    constexpr int smem = ring_bytes(0, false);
+    auto k = heat_march_reduce_kernel<HAS_D, false, 0, true>;
+    k<<<march_grid(k, g, smem, true), kThreads, smem, s>>>(p, g, partials, nullptr, nullptr, 0, nullptr, nullptr);
+    per_sample_items_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(partials, g.n_seg_items / p.B, p.B, out);
+    return check_launch("dpde_heat_residual_sq (march)");
+}
+
+template <bool HAS_D>
+int launch_march_per_sample_vjp(const Params& p, const double* upstream, float* g_u, float* g_dudt, cudaStream_t s) {
+    const MarchGeom g = march_geometry(p, true);
+    constexpr int smem = ring_bytes(0, true);
+    auto k = heat_march_vjp_kernel<HAS_D, false, 0, true>;
+    k<<<march_grid(k, g, smem, true), kThreads, smem, s>>>(p, g, nullptr, upstream, g_u, g_dudt);
+    return check_launch("dpde_heat_residual_sq_vjp (march)");
+}
+
 View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }
 
 int validate_and_fill(const dpde_guidance_desc* d, int tile_pix, Params& p, const char* who) {
@@ -1074,7 +1123,11 @@ int dpde_laplacian(const void* u, void* out, int32_t dtype, int64_t planes, int3
     return check_launch("dpde_laplacian");
 }
 
-size_t dpde_heat_residual_sq_workspace_bytes(int32_t B) { return (size_t)(B > 0 ? B : 0) * kPerSampleBlocks * sizeof(double); }
+size_t dpde_heat_residual_sq_workspace_bytes(int32_t B, int32_t Cu, int32_t H, int32_t W) {
+    if (B < 1 || Cu < 1 || H < 1 || W < 1) return 0;
+    const int64_t a = (int64_t)B * kPerSampleBlocks, b = per_sample_item_bound(B, Cu, H, W);
+    return (size_t)(a > b ? a : b) * sizeof(double);
+}
 
 int dpde_heat_residual_sq(const void* u, const void* dudt, int32_t dtype, int32_t B, int32_t Cu, int32_t H, int32_t W, int64_t sb_u,
                           int64_t sc_u, int64_t sb_d, int64_t sc_d, const double* alpha, double dx, void* workspace, double* out,
@@ -1087,6 +1140,12 @@ int dpde_heat_residual_sq(const void* u, const void* dudt, int32_t dtype, int32_
     if (B > 65535) return fail(DPDE_ERR_UNSUPPORTED, "dpde_heat_residual_sq: at most 65535 samples per call");
     const double inv = 1.0 / (dx * dx);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const Params p = per_sample_params(u, dudt, dtype, B, Cu, H, W, sb_u, sc_u, sb_d, sc_d, alpha, dx);
+        if (march_eligible(p, nullptr, nullptr))
+            return dudt ? launch_march_per_sample_reduce<true>(p, reinterpret_cast<double*>(workspace), out, s)
+                        : launch_march_per_sample_reduce<false>(p, reinterpret_cast<double*>(workspace), out, s);
+    }
     int64_t nblk = ((int64_t)Cu * H * W + 8 * kThreads - 1) / (8 * kThreads);   // ~8 pixels per thread
     if (nblk > kPerSampleBlocks) nblk = kPerSampleBlocks;
     const dim3 grid((unsigned)nblk, (unsigned)B);
@@ -1113,6 +1172,12 @@ int dpde_heat_residual_sq_vjp(const void* u, const void* dudt, int32_t dtype, in
     if (blocks > cap) blocks = cap;
     const double inv = 1.0 / (dx * dx);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const Params p = per_sample_params(u, dudt, dtype, B, Cu, H, W, sb_u, sc_u, sb_d, sc_d, alpha, dx);
+        if (march_eligible(p, g_u, g_dudt))
+            return dudt ? launch_march_per_sample_vjp<true>(p, upstream, (float*)g_u, (float*)g_dudt, s)
+                        : launch_march_per_sample_vjp<false>(p, upstream, (float*)g_u, (float*)g_dudt, s);
+    }
     if (dtype == DPDE_F32)
         heat_residual_sq_vjp_kernel<float><<<(int)blocks, kThreads, 0, s>>>((const float*)u, (const float*)dudt, sb_u, sc_u, sb_d, sc_d, alpha, upstream, B, Cu, H, W, inv, (float*)g_u, (float*)g_dudt);
     else

@@ -233,7 +233,10 @@ __device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, 
 // ---------------------------------------------------------------------------------------------------------
 // pass 1 (fast): S_a, S_u, S_pde
 // ---------------------------------------------------------------------------------------------------------
-template <bool HAS_D, bool HAS_O, int PA>
+// PS (per-sample mode, training loss models/loss.py:143): no global sums -- every row-segment item writes its own
+// sum of squared residuals to partials[item] (items of sample b are b, b + B, b + 2 B, ...: per_sample_items_kernel adds
+// them in that order), nothing else is touched.
+template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
 __global__ void __launch_bounds__(kThreads, 3)
 heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g,
                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
@@ -320,8 +323,16 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
             ub = uc;
         }
         cp_async_wait<0>();
+        if (PS) {   // segmented (LW-lane) butterfly, lane 0 of every segment owns the item's sum
+            double v = s_p;
+            for (int o = LW >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LW);
+            const unsigned si = (unsigned)wi * g.segs_per_warp + (lane >> g.lw_log2);
+            if ((lane & (LW - 1)) == 0 && si < (unsigned)g.n_seg_items) partials[si] = v;
+            s_p = 0.0;
+        }
     };
     run_interleaved(warp0, nwarps, g.n_warp_items, (PA == 0 && p.has_a) ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+    if (PS) return;
 
     block_sum3(s_a, s_u, s_p, scratch);
     if (tid == 0) {
@@ -353,14 +364,17 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 (fast): seed gradient
 // ---------------------------------------------------------------------------------------------------------
-template <bool HAS_D, bool HAS_O, int PA>
+// PS (per-sample mode): `upstream` holds one seed per sample, c_p of an item = 2 upstream[b] (d r^2 / d r), no
+// observation terms, `scal` is not read.
+template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
 __global__ void __launch_bounds__(kThreads, 2)
 heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, const double* __restrict__ scal,
                       const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
     extern __shared__ __align__(16) unsigned char ring_mem[];
     const int tid = threadIdx.x, lane = tid & 31;
-    const double up = upstream ? __ldg(upstream) : 1.0;
-    const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
+    const double up = (!PS && upstream) ? __ldg(upstream) : 1.0;
+    const double c_a = PS ? 0.0 : __ldg(scal + 4) * up, c_u = PS ? 0.0 : __ldg(scal + 5) * up;
+    double c_p = PS ? 0.0 : __ldg(scal + 6) * up;
     const float* x0 = reinterpret_cast<const float*>(p.x0.p);
     const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
     const int64_t plane = (int64_t)p.H * p.W;
@@ -415,6 +429,7 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
         float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane : nullptr;
         float* gaout = PA ? g_x0 + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;                 // paired a-plane
         float* gadout = (PA && g_dxdt) ? g_dxdt + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;
+        if (PS) c_p = 2.0 * __ldg(upstream + m.b);
         const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
         const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
         D4v ua = widen(ring.direct_u(p, m.ys - 2)), ub = widen(ring.direct_u(p, m.ys - 1));

@@ -35,7 +35,7 @@ class _HeatResidualSq(torch.autograd.Function):
         if a64.shape != (B,):
             raise RuntimeError(f"heat_residual_sq: alpha must have shape ({B},), got {tuple(a64.shape)}")
         out = torch.empty(B, dtype=torch.float64, device=u.device)
-        ws = torch.empty(max(_ffi.lib().dpde_heat_residual_sq_workspace_bytes(B), 8), dtype=torch.uint8, device=u.device)
+        ws = torch.empty(max(_ffi.lib().dpde_heat_residual_sq_workspace_bytes(B, Cu, H, W), 8), dtype=torch.uint8, device=u.device)
         _ffi.call("dpde_heat_residual_sq", uv.data_ptr(), dv.data_ptr() if dv is not None else None, _DTYPES[u.dtype], B, Cu, H, W,
                   uv.stride(0), uv.stride(1), dv.stride(0) if dv is not None else 0, dv.stride(1) if dv is not None else 0,
                   a64.data_ptr(), float(dx), ws.data_ptr(), out.data_ptr(), _stream())

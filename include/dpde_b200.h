@@ -124,8 +124,9 @@ int dpde_laplacian(const void* u, void* out, int32_t dtype, int64_t planes, int3
    out[b] = sum_{c,h,w} (dudt - alpha_b laplacian(u, dx))^2  for u, dudt (B, Cu, H, W) with rows contiguous and free
    batch / channel strides (x_0star[:, ch_a:] is a channel-slice view), alpha_b = labels[b, 1].  The caller applies
    1/(H W), the mean / sum over (C, H, W) and pde_loss_coeff / sigma^2 (models/loss.py:143-149) with torch ops.
-   `workspace`: dpde_heat_residual_sq_workspace_bytes(B) bytes of device scratch.  dudt == NULL means zeros. */
-size_t dpde_heat_residual_sq_workspace_bytes(int32_t B);
+   `workspace`: dpde_heat_residual_sq_workspace_bytes(B, Cu, H, W) bytes of device scratch.  dudt == NULL means zeros.
+   Eligible layouts (as dpde_set_fast_path) run on the row-marching kernels, the rest on a generic grid-stride kernel. */
+size_t dpde_heat_residual_sq_workspace_bytes(int32_t B, int32_t Cu, int32_t H, int32_t W);
 int dpde_heat_residual_sq(const void* u, const void* dudt, int32_t dtype, int32_t B, int32_t Cu, int32_t H, int32_t W,
                           int64_t stride_b_u, int64_t stride_c_u, int64_t stride_b_dudt, int64_t stride_c_dudt,
                           const double* alpha, double dx, void* workspace, double* out, dpde_stream_t stream);
