@@ -724,13 +724,17 @@ inline int pairing(const Params& p, bool vjp) {
 
 template <typename K>
 int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
-    // opt in to > 48 KB dynamic shared memory once per kernel instantiation, then size a persistent grid
-    static thread_local const void* configured[64] = {nullptr};
+    // opt in to > 48 KB dynamic shared memory once per kernel instantiation AND device (the attribute is per device;
+    // a process may drive several GPUs), then size a persistent grid
+    static thread_local const void* configured[16][64] = {{nullptr}};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto& mine = configured[dev & 15];
     bool seen = false;
-    for (const void* k : configured) seen = seen || k == (const void*)kernel;
-    if (!seen) {
+    for (const void* k : mine) seen = seen || k == (const void*)kernel;
+    if (!seen || dev > 15) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        for (auto& k : configured)
+        for (auto& k : mine)
             if (!k) { k = (const void*)kernel; break; }
     }
     int occ = 0;
@@ -819,12 +823,15 @@ LlgGeom llg_geometry(const Params& p) {
 
 template <typename K>
 int llg_grid(K kernel, int smem, int64_t cta_items) {
-    static thread_local const void* configured[16] = {nullptr};
+    static thread_local const void* configured[16][16] = {{nullptr}};   // per device, as in march_grid
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto& mine = configured[dev & 15];
     bool seen = false;
-    for (const void* k : configured) seen = seen || k == (const void*)kernel;
-    if (!seen) {
+    for (const void* k : mine) seen = seen || k == (const void*)kernel;
+    if (!seen || dev > 15) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        for (auto& k : configured)
+        for (auto& k : mine)
             if (!k) { k = (const void*)kernel; break; }
     }
     int occ = 0;

@@ -161,3 +161,30 @@ def test_two_process_batch_shards():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "shard_check ok" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_one_process_two_devices():
+    """The > 48 KB shared-memory opt-in of the fast-path kernels is a per-device attribute: the same process must be able
+    to run them on a second GPU (heat marching kernels and LLG tiles), with the same results."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants
+    from dynamical_pde_diffusion_b200._ffi import PDE_HEAT, PDE_LLG_RESIDUAL
+
+    g = torch.Generator().manual_seed(2)
+    B, H, W = 2, 40, 260
+    outs = {}
+    for kind, C_, ch_a in ((PDE_HEAT, 2, 1), (PDE_LLG_RESIDUAL, 6, 3)):
+        x0, dxdt = torch.randn(B, C_, H, W, generator=g), 0.1 * torch.randn(B, C_, H, W, generator=g)
+        obs_a, obs_u = torch.randn(1, ch_a, H, W, generator=g), torch.randn(1, C_ - ch_a, H, W, generator=g)
+        mask = torch.rand(H, W, generator=g) < 0.2
+        coef = torch.rand(B, generator=g).double() if kind == PDE_HEAT else (1e4 * torch.randn(B, 3, generator=g)).double()
+        for d in (0, 1):
+            dev = torch.device("cuda", d)
+            with torch.cuda.device(dev):
+                eng = GuidanceEngine(B, C_, ch_a, H, W, kind, dev, obs_a=obs_a.to(dev), mask_a=mask.to(dev), obs_u=obs_u.to(dev),
+                                     mask_u=mask.to(dev), sample_coef=coef.to(dev), dx=1.0 / (H - 1) if kind == PDE_HEAT else 500e-9 / 64,
+                                     llg=LLGConstants())
+                gx, _ = eng.seed(x0.to(dev), dxdt.to(dev), (5.0, 0.5, 7.0))
+                torch.cuda.synchronize(dev)
+                outs[(kind, d)] = (gx.cpu(), eng.scalars[:4].cpu())
+        assert torch.equal(outs[(kind, 0)][0], outs[(kind, 1)][0]) and torch.equal(outs[(kind, 0)][1], outs[(kind, 1)][1])
