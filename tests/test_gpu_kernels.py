@@ -310,6 +310,31 @@ def test_llg_residual_guidance(shape, K0, kernel_path):
     _close(gd[:, ch_a:], gd_ref, RTOL32, "llg residual d/d dmdt")
 
 
+@pytest.mark.parametrize("kind_name", ["heat", "llg_residual"])
+def test_absent_time_derivative_equals_zeros(kind_name, kernel_path):
+    """dxdt == NULL (X_and_dXdt_dummy without the zeros tensor) must give what an all-zero dxdt gives, on both kernel paths;
+    per-channel (ch, H, W) masks and per-sample observations exercise the stride handling of the fast paths."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants
+    from dynamical_pde_diffusion_b200._ffi import PDE_HEAT, PDE_LLG_RESIDUAL
+
+    dev, w = _dev(), (3.0, 0.7, 11.0)
+    kind, ch_a, cu, dx = (PDE_HEAT, 1, 1, 1 / 39) if kind_name == "heat" else (PDE_LLG_RESIDUAL, 3, 3, 500e-9 / 64)
+    B, H, W = 3, 40, 72
+    g = torch.Generator().manual_seed(17)
+    x0 = torch.randn(B, ch_a + cu, H, W, generator=g).to(dev)
+    obs_a, obs_u = torch.randn(B, ch_a, H, W, generator=g).to(dev), torch.randn(B, cu, H, W, generator=g).to(dev)
+    mask_a, mask_u = (torch.rand(ch_a, H, W, generator=g) < 0.3).to(dev), (torch.rand(cu, H, W, generator=g) < 0.2).to(dev)
+    coef = torch.rand(B, generator=g).double().to(dev) if kind == PDE_HEAT else (1e4 * torch.randn(B, 3, generator=g)).double().to(dev)
+    outs = []
+    for dxdt in (None, torch.zeros_like(x0)):
+        eng = GuidanceEngine(B, ch_a + cu, ch_a, H, W, kind, dev, obs_a=obs_a, mask_a=mask_a, obs_u=obs_u, mask_u=mask_u,
+                             sample_coef=coef, dx=dx, llg=LLGConstants())
+        gx, _ = eng.seed(x0, dxdt, w)
+        outs.append((gx.clone(), eng.scalars[:4].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.isfinite(outs[0][0]).all()
+
+
 def test_level1_llg_residual_matches_oracle_autograd():
     import dynamical_pde_diffusion_b200 as dp
 
