@@ -47,14 +47,16 @@ def observation_metrics(obs: torch.Tensor, samples: torch.Tensor):
 
 
 def test_loop(sampler, testloader, zeta_a, zeta_u, zeta_pde, mask_a=None, mask_u=None, max_num_samples=1000, *, group=None,
-              log=None, save_path=None):
+              log=None, save_path=None, seed=None):
     """Evaluate ``sampler`` on the observations of ``testloader`` (any iterable of dicts with ``A`` (1,c,H,W), ``U``
     (1,c,H,W) and ``labels`` (1,label_dim) or None, as the reference's DataLoader yields with batch_size 1).
 
     Returns a dict of numpy arrays ``MAE``, ``denom_abs``, ``std`` (n, C, H, W) and ``denom_range`` (n, C) -- the
     contents of the reference's ``validation_data.npz`` (``model_testing.py:228-229``; written when ``save_path`` is
     given, by rank 0).  ``log(dict)`` receives the two per-observation scalars the reference sends to wandb
-    (``model_testing.py:217-220``); they are read back from the device only when a logger is supplied.
+    (``model_testing.py:217-220``); they are read back from the device only when a logger is supplied.  With ``seed`` the
+    latents of observation i come from ``Generator(seed + i)`` -- the result then does not depend on the number of ranks;
+    without it they are the sampler's own ``torch.randn`` draws, as in the reference.
     """
     import torch.distributed as dist
 
@@ -89,8 +91,12 @@ def test_loop(sampler, testloader, zeta_a, zeta_u, zeta_pde, mask_a=None, mask_u
         if labels is not None:
             labels = labels.expand(sampler.num_samples, -1)            # model_testing.py:195-196
         A_d, U_d = A.to(dev, non_blocking=True), U.to(dev, non_blocking=True)
+        extra = {}
+        if seed is not None:
+            from .distributed import full_latents
+            extra["latents"] = full_latents(sampler.num_samples, C_, (H, W), seed + i)
         samples, _ = sampler.sample(labels=labels, obs_a=A_d, obs_u=U_d, mask_a=mask_a_d, mask_u=mask_u_d, zeta_a=zeta_a,
-                                    zeta_u=zeta_u, zeta_pde=zeta_pde, return_losses=False, to_cpu=False)
+                                    zeta_u=zeta_u, zeta_pde=zeta_pde, return_losses=False, to_cpu=False, **extra)
         obs = torch.cat([A_d, U_d], dim=1).to(samples.dtype)
         MAE[k], d_abs[k], d_rng[k], std[k] = observation_metrics(obs, samples)
         if log is not None:

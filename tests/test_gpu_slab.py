@@ -188,3 +188,13 @@ def test_one_process_two_devices():
                 torch.cuda.synchronize(dev)
                 outs[(kind, d)] = (gx.cpu(), eng.scalars[:4].cpu())
         assert torch.equal(outs[(kind, 0)][0], outs[(kind, 1)][0]) and torch.equal(outs[(kind, 0)][1], outs[(kind, 1)][1])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_process_evaluation_loop():
+    """evaluation.test_loop on two ranks: round-robin observations + one all-gather equal the single-process loop."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29661", os.path.join(ROOT, "scripts", "eval_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "eval_check ok" in r.stdout
