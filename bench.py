@@ -199,7 +199,7 @@ def config_dict(args, batch_per_gpu):
                         "LLG m x H_eff residual: exchange + uniaxial anisotropy (K0 = 0 as the reference) + applied field",
             "parallelism": f"batch-shard x{args.gpus}, independent shards",
             "denoiser_conv_precision": "ieee fp32" if args.ieee else "tf32 (as the reference's sampling_context, sample.py:626-630)",
-            "cache": "inputs of every step are freshly produced tensors; per-step working set (denoiser activations, >10 GB) exceeds the 126 MB L2"}
+            "cache": "inputs of every step are freshly produced tensors; per-step working set (denoiser activations, ~1 GiB per sample: 64 GiB at batch 64) exceeds the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------------------
