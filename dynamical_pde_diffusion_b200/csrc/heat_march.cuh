@@ -124,6 +124,8 @@ struct RowRing {
     const float *u, *du, *ob, *a, *oa;
     const unsigned char *mk, *ma;
     int row0;
+    int off_run;                             // fast items: element offset of the next ring element to issue
+    bool fast;                               // every row this item touches is inside the grid and the buffer: no reflection
 
     static __device__ __forceinline__ unsigned slot16(int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); }
     static __device__ __forceinline__ unsigned slot4(int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); }
@@ -131,8 +133,17 @@ struct RowRing {
     // start the copies of element s (fields selected by warp-uniform flags); always commits exactly one group.
     // fo also selects the a-plane fields: they are consumed together with the observation of the same row.
     int colc;                                // the lane's first column (clamped to 0 for idle lanes)
-    __device__ __forceinline__ void issue(const Params& p, int s, bool fu, bool fd, bool fo) const {
-        const int off = row_offset(p, row0 + s);
+    // Start of a work item whose ring elements 0 .. last cover rows first .. first + last.  Interior items (all but the
+    // first and last chunk of a plane) need no reflection: the row offset just advances by W per element.
+    __device__ __forceinline__ void begin_item(const Params& p, int first, int last) {
+        row0 = first;
+        const int g0 = first + p.yg0, g1 = first + last + p.yg0;
+        fast = __all_sync(0xffffffffu, g0 >= 0 && g1 <= p.Hg - 1 && first >= 0 && first + last <= p.H - 1);
+        off_run = first * p.W;
+    }
+    __device__ __forceinline__ void issue(const Params& p, int s, bool fu, bool fd, bool fo) {
+        const int off = fast ? off_run : row_offset(p, row0 + s);
+        off_run += p.W;
         if (fu) cp_async16(su + slot16(s), u + off);
         if (HAS_D && fd) cp_async16(sd + slot16(s), du + off);
         if (HAS_O && fo) {
@@ -276,8 +287,8 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
         ring.bind(p, m, x0, dxp);
-        ring.row0 = m.ys;
         const int n_it = g.R, n_el = g.R + 1;
+        ring.begin_item(p, m.ys, n_el - 1);
 #pragma unroll
         for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
         const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
@@ -419,8 +430,8 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
         ring.bind(p, m, x0, dxp);
-        ring.row0 = m.ys - 2;
         const int n_it = g.R + 2;
+        ring.begin_item(p, m.ys - 2, n_it + 1);
         // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
 #pragma unroll
         for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
