@@ -20,6 +20,8 @@
 // chosen from W so narrow grids such as the reference's 64x16 LLG film keep all lanes busy); a persistent grid
 // (SM count x occupancy) strides over tiles; consecutive lanes touch consecutive columns (coalesced 128 B rows).
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace dpde {
@@ -648,12 +650,15 @@ heat_residual_sq_vjp_kernel(const T* __restrict__ u, const T* __restrict__ dudt,
 // =========================================================================================================
 // host side
 // =========================================================================================================
-bool g_fast_path = true;
+// Test / tuning hooks (dpde_set_fast_path, dpde_set_tuning): process-wide, read once per launch.  They are atomics so a
+// concurrent setter is not a data race, but a launch in flight on another thread may see either value: set them
+// before the threads that launch start (the tests and scripts/kernel_probe.py are their only callers).
+std::atomic<bool> g_fast_path{true};
 // experiment knobs (dpde_set_tuning): [0] strip layout 0 = per pass (reduce 120 columns + 1 halo lane, VJP 112 + 2,
 // sector aligned), 1 = 120 + 1 in both, 2 = 112 + 2 in both;
 // [1] unused; [2] rows per chunk (0 = automatic); [3] / [4] 1 = pair a-planes with u-planes in the
 // reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s)
-int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+std::atomic<int> g_tuning[8] = {};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
@@ -1050,9 +1055,7 @@ using namespace dpde;
 extern "C" {
 
 int dpde_set_fast_path(int enable) {
-    const int old = g_fast_path ? 1 : 0;
-    g_fast_path = enable != 0;
-    return old;
+    return g_fast_path.exchange(enable != 0) ? 1 : 0;
 }
 
 int dpde_set_tuning(int key, int value) {

@@ -196,18 +196,24 @@ def randomize_zero_init(net: nn.Module, seed: int = 0, scale: float = 1.0) -> nn
 
 
 class PointwiseDenoiser(nn.Module):
-    """Analytic stand-in D(x; sigma) = c_skip x + c_out tanh(c_in x) (no spatial coupling, no parameters).
-
-    Used for the 4096^2 row-slab configuration: it keeps the sampler's data flow (two evaluations and a
-    double backward per step) while every spatial dependency of the step sits in the guidance kernels.
-    """
+    """``D(x; sigma) = c_skip(sigma) x + c_out(sigma) tanh(c_in(sigma) x + t)`` with EDM preconditioning coefficients
+    (``models/nets.py:352-366``) and the label's time entry as a bias: local, differentiable, label dependent (so the
+    finite-difference time derivative is not identically zero).  A stand-in for throughput and parity runs on grids
+    where the reference U-Net cannot run (config 5, 4096^2: activations exceed HBM and GroupNorm is a global
+    statistic, ``models/nets.py:172-175``); not a trained model.  No spatial coupling, no parameters."""
 
     def __init__(self, sigma_data: float = 0.5):
         super().__init__()
         self.sigma_data = sigma_data
 
-    def forward(self, x, sigma, labels=None, **_):
-        s = torch.reshape(sigma, (-1, 1, 1, 1))
+    def forward(self, x, sigma, labels=None, **kw):
+        s = sigma.to(x.dtype).reshape(-1, 1, 1, 1)
         sd = self.sigma_data
-        den = s ** 2 + sd ** 2
-        return (sd ** 2 / den) * x + (s * sd / torch.sqrt(den)) * torch.tanh(x / torch.sqrt(den))
+        c_skip = sd ** 2 / (s ** 2 + sd ** 2)
+        c_out = s * sd / (s ** 2 + sd ** 2).sqrt()
+        c_in = 1 / (sd ** 2 + s ** 2).sqrt()
+        t = labels[:, 0].to(x.dtype).reshape(-1, 1, 1, 1) if labels is not None else 0.0
+        return c_skip * x + c_out * torch.tanh(c_in * x + t)
+
+    def round_sigma(self, sigma):
+        return torch.as_tensor(sigma)

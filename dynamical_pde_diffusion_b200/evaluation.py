@@ -47,7 +47,22 @@ def observation_metrics(obs: torch.Tensor, samples: torch.Tensor):
 
 
 def test_loop(sampler, testloader, zeta_a, zeta_u, zeta_pde, mask_a=None, mask_u=None, max_num_samples=1000, *, group=None,
-              log=None, save_path=None, seed=None):
+              log=None, save_path=None, seed=None, tf32=True, keep_on_device=False):
+    """``model_testing.test_loop`` (``model_testing.py:162-239``): sampling runs inside :class:`sampling_context` as in
+    the reference (``model_testing.py:186``) -- the net is put in ``eval()`` mode and moved to ``sampler.device``, cuDNN
+    convolutions run in TF32 unless ``tf32=False``, and the net returns to the CPU afterwards unless
+    ``keep_on_device=True``.  See :func:`_test_loop` for the arguments and the returned arrays."""
+    from .sampler import sampling_context
+
+    if torch.device(sampler.device).type != "cuda":
+        raise RuntimeError(f"dpde_b200.evaluation.test_loop runs on CUDA devices only (got {sampler.device}); there is no CPU path")
+    with sampling_context(sampler, tf32=tf32, keep_on_device=keep_on_device):
+        return _test_loop(sampler, testloader, zeta_a, zeta_u, zeta_pde, mask_a, mask_u, max_num_samples, group=group, log=log,
+                          save_path=save_path, seed=seed)
+
+
+def _test_loop(sampler, testloader, zeta_a, zeta_u, zeta_pde, mask_a=None, mask_u=None, max_num_samples=1000, *, group=None,
+               log=None, save_path=None, seed=None):
     """Evaluate ``sampler`` on the observations of ``testloader`` (any iterable of dicts with ``A`` (1,c,H,W), ``U``
     (1,c,H,W) and ``labels`` (1,label_dim) or None, as the reference's DataLoader yields with batch_size 1).
 

@@ -120,21 +120,25 @@ class GuidanceEngine:
     """
 
     def __init__(self, B, C_, ch_a, H, W, pde_kind, device, *, obs_a=None, mask_a=None, obs_u=None, mask_u=None,
-                 sample_coef=None, dx=0.0, llg: LLGConstants | None = None, slab=None):
+                 sample_coef=None, dx=0.0, llg: LLGConstants | None = None, slab=None, has_flags=None):
+        """``has_flags = (has_a, has_u)`` overrides the local empty-mask test (``sample.py:339,341``) with a decision
+        taken elsewhere -- globally over the ranks of a coupled batch shard or of a row-slab decomposition."""
         self.B, self.C, self.ch_a, self.H, self.W, self.kind, self.device = B, C_, ch_a, H, W, pde_kind, device
         d = GuidanceDesc()
         d.B, d.C, d.ch_a, d.H, d.W, d.pde_kind = B, C_, ch_a, H, W, pde_kind
         self._keep = []
         cu = C_ - ch_a
         d.has_a = d.has_u = 0
+        if has_flags is None and slab is not None:
+            has_flags = (slab["has_a"], slab["has_u"])
         if mask_a is not None and ch_a > 0:
-            d.has_a = int(bool((mask_a.sum() > 0).item())) if slab is None else int(slab["has_a"])
+            d.has_a = int(bool((mask_a.sum() > 0).item())) if has_flags is None else int(bool(has_flags[0]))
             if d.has_a:
                 d.obs_a, t1 = broadcast_view(obs_a, B, ch_a, H, W, "obs")
                 d.mask_a, t2 = broadcast_view(mask_a, B, ch_a, H, W, "mask")
                 self._keep += [t1, t2]
         if mask_u is not None and cu > 0:
-            d.has_u = int(bool((mask_u.sum() > 0).item())) if slab is None else int(slab["has_u"])
+            d.has_u = int(bool((mask_u.sum() > 0).item())) if has_flags is None else int(bool(has_flags[1]))
             if d.has_u:
                 d.obs_u, t1 = broadcast_view(obs_u, B, cu, H, W, "obs")
                 d.mask_u, t2 = broadcast_view(mask_u, B, cu, H, W, "mask")

@@ -81,6 +81,32 @@ def X_and_dXdt(net, x, sigma, labels):
     return torch.func.jvp(f, (t0,), (torch.ones_like(t0),))
 
 
+class sampling_context:
+    """``sampling_context`` of the reference (``sample.py:622-637``): cuDNN convolutions in TF32, the denoiser in
+    ``eval()`` mode and on the sampler's device while the block runs.  On exit the precision setting is restored and --
+    as the reference does -- the net goes back to the CPU (``keep_on_device=True`` skips that move and the cache flush,
+    for callers that sample repeatedly).  ``tf32=False`` leaves the precision alone (parity runs use IEEE fp32)."""
+
+    def __init__(self, sampler, tf32: bool = True, keep_on_device: bool = False):
+        self.sampler, self.tf32, self.keep = sampler, tf32, keep_on_device
+
+    def __enter__(self):
+        self.prev = torch.backends.cudnn.conv.fp32_precision
+        if self.tf32:
+            torch.backends.cudnn.conv.fp32_precision = "tf32"
+        self.was_training = self.sampler.net.training
+        self.sampler.net.eval()
+        self.sampler.net.to(self.sampler.device)
+        return self.sampler
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        torch.backends.cudnn.conv.fp32_precision = self.prev
+        if not self.keep:
+            self.sampler.net.to(torch.device("cpu"))
+            torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+
+
 class _EulerPredict(torch.autograd.Function):
     """x_eu32 = fp32(x_cur + h (x_cur - x0)/s_cur) as a graph node between the two denoiser evaluations.
 
@@ -253,8 +279,20 @@ class JointSampler(Sampler):
         elif kind == PDE_LLG_RESIDUAL:
             llg = self.loss_kwargs.get("consts", LLGConstants())
             coef, dx = labels[:, -3:].to(F64) / (1000 * llg.mu0), float(self.loss_kwargs["dx"])
+        has_flags = None
+        if self.coupled:
+            # one batch-B run over all ranks: the empty-mask branches (sample.py:339,341) are decided on the GLOBAL batch
+            # (a rank whose per-sample mask shard happens to be empty must still take part in the norm), and an arbitrary
+            # loss_fn would be evaluated per shard -- its term cannot be coupled, so it is refused
+            if kind is None:
+                raise RuntimeError("JointSampler(coupled=True) needs one of the fused residuals (heat_loss2, llg_loss2, "
+                                   "llg_residual_loss): an arbitrary loss_fn is evaluated per shard and cannot be coupled")
+            import torch.distributed as dist
+            flags = torch.tensor([float(mask_a.sum() > 0), float(mask_u.sum() > 0)], device=dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+            has_flags = (bool(flags[0] > 0), bool(flags[1] > 0))
         engine = GuidanceEngine(B, C_, ch_a, H, W, kind if kind is not None else PDE_NONE, dev, obs_a=obs_a, mask_a=mask_a,
-                                obs_u=obs_u, mask_u=mask_u, sample_coef=coef, dx=dx, llg=llg)
+                                obs_u=obs_u, mask_u=mask_u, sample_coef=coef, dx=dx, llg=llg, has_flags=has_flags)
         x64 = torch.empty((B, C_, H, W), dtype=F64, device=dev)
         x32 = torch.empty((B, C_, H, W), dtype=F32, device=dev)
         _ffi.call("dpde_sampler_init", latents.data_ptr(), sigmas[0], x64.data_ptr(), x32.data_ptr(), x64.numel(), _stream())

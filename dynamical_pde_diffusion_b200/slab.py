@@ -38,6 +38,7 @@ import numpy as np
 import torch
 
 from . import _ffi
+from .denoiser import PointwiseDenoiser  # noqa: F401  (re-exported: the stand-in denoiser of config 5)
 from .distributed import _all_gather, shard_bounds
 from .ops import GuidanceEngine, LLGConstants, _stream
 from .sampler import F32, F64, JointSampler, _pde_kind_of
@@ -204,9 +205,16 @@ class PeerHaloExchange:
                 self.peers[nb] = others[nb].buf.ptr
 
     def close(self):
+        """Unmap the neighbours' allocations (collective protocol: every rank closes, barrier, then :meth:`free`)."""
         for p in self._opened:
             _ffi.check(_ffi.lib().dpde_peer_close(p))
         self._opened = []
+        self.peers = {}
+
+    def free(self):
+        """Release this rank's exportable allocation.  Only after every neighbour has closed its mapping."""
+        self.x64, self.x32, self.status = [], [], None
+        self.buf.free()
 
     # ---- per step -----------------------------------------------------------------------------------------
     def push(self, parity: int):
@@ -244,35 +252,12 @@ class PeerHaloExchange:
         _ffi.call("dpde_flag_wait", arr, len(flags), self.epoch, self.timeout_s, self.status.data_ptr(), _stream())
 
     def check(self):
-        """Host-side check of the wait status (one sync; call at the end of a run)."""
+        """Host-side check of the wait status (one sync; call at the end of a run).  The status word is cleared so a
+        later run on this exchange object starts clean."""
         if int(self.status.item()) != 0:
-            raise _ffi.DpdeError("dpde_flag_wait timed out: a neighbouring rank never pushed its halo rows")
-
-
-# ---------------------------------------------------------------------------------------------------------
-# pointwise stand-in denoiser for grids the U-Net cannot handle
-# ---------------------------------------------------------------------------------------------------------
-class PointwiseDenoiser(torch.nn.Module):
-    """``D(x; sigma) = c_skip(sigma) x + c_out(sigma) tanh(c_in(sigma) x + t)`` with EDM preconditioning coefficients
-    (``models/nets.py:352-366``) and the label's time entry as a bias: local, differentiable, label dependent (so the
-    finite-difference time derivative is not identically zero).  A stand-in for throughput and parity runs on grids
-    where the reference U-Net cannot run; not a trained model."""
-
-    def __init__(self, sigma_data: float = 0.5):
-        super().__init__()
-        self.sigma_data = sigma_data
-
-    def forward(self, x, sigma, labels=None, **kw):
-        s = sigma.to(x.dtype).reshape(-1, 1, 1, 1)
-        sd = self.sigma_data
-        c_skip = sd ** 2 / (s ** 2 + sd ** 2)
-        c_out = s * sd / (s ** 2 + sd ** 2).sqrt()
-        c_in = 1 / (sd ** 2 + s ** 2).sqrt()
-        t = labels[:, 0].to(x.dtype).reshape(-1, 1, 1, 1) if labels is not None else 0.0
-        return c_skip * x + c_out * torch.tanh(c_in * x + t)
-
-    def round_sigma(self, sigma):
-        return torch.as_tensor(sigma)
+            self.status.zero_()
+            raise _ffi.DpdeError("dpde_flag_wait timed out: a neighbouring rank never pushed its halo rows; the run's "
+                                 "ghost rows were stale from that step on and its result must be discarded")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -283,10 +268,18 @@ class SlabJointSampler(JointSampler):
     observations, masks, latents); ``sample()`` returns this rank's owned rows unless ``gather=True``.
 
     ``plan`` fixes the decomposition; ``transport`` is ``"peer"`` (NVLink peer-memory kernel, default on CUDA with
-    an initialised process group), ``"dist"`` (torch.distributed send/recv) or a ready transport object."""
+    an initialised process group), ``"dist"`` (torch.distributed send/recv) or ``"none"`` (no exchange at all: only
+    legal for a single-rank plan).  Anything else raises: a silently skipped exchange would leave the ghost rows at
+    their initial values for the whole run."""
+
+    TRANSPORTS = ("peer", "dist", "none")
 
     def __init__(self, *args, plan: SlabPlan, transport="peer", group=None, allreduce=None, **kw):
         super().__init__(*args, **kw)
+        if transport not in self.TRANSPORTS:
+            raise ValueError(f"SlabJointSampler: unknown transport {transport!r}; choose one of {self.TRANSPORTS}")
+        if transport == "none" and plan.world > 1:
+            raise ValueError("SlabJointSampler: transport 'none' exchanges no ghost rows and is only valid for a single-rank plan")
         self.plan, self.transport_kind, self.group = plan, transport, group
         self._allreduce_fn = allreduce
         self.peer = None
@@ -412,6 +405,19 @@ class SlabJointSampler(JointSampler):
         if gather and self.plan.world > 1:
             x = gather_rows(x, self.plan, self.group)
         return x.cpu(), losses
+
+    def release(self):
+        """Unmap the neighbours' buffers, then (after a barrier: every mapping must be closed before its owner frees)
+        free this rank's exportable allocation."""
+        if self.peer is None:
+            return
+        self.peer.close()
+        if self.plan.world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+        self.peer.free()
+        self.peer = None
 
     def sample(self, labels, obs_a, obs_u, mask_a, mask_u, zeta_a, zeta_u, zeta_pde, return_losses=False,
                num_steps=None, sigma_min=None, sigma_max=None, rho=None, *, latents=None, generator=None, gather=False):

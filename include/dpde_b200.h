@@ -85,13 +85,15 @@ const char* dpde_last_error(void);
 /* Kernel selection: 1 (default) lets eligible problems (fp32 fields, W % 4 == 0, 16-byte aligned operands, fp32
    observations, uint8 masks) take the fast paths -- register row-marching kernels for the heat residual, convert-once
    shared-memory tiles for the LLG m x H_eff residual, 128-bit streaming for the soft-norm loss; 0 forces the generic
-   tile kernels, which accept every layout.  Both give the same results (tests run both).  Returns the previous setting. */
+   tile kernels, which accept every layout.  Both give the same results (tests run both).  Returns the previous setting.
+   TEST / TUNING HOOK: process-wide (an atomic, read once per launch); set it before the launching threads start. */
 int dpde_set_fast_path(int enable);
 
 /* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 (default) =
    per pass: 120 columns + 1 halo lane in the reduce pass, 112 + 2 sector aligned in the VJP; 1 / 2 force one of them), key 2 rows per chunk (0 = automatic: up to 128 in the
    VJP, 64 in the reduce pass), keys 3 / 4 = 1 pair every a-plane with the u-plane of the same index in the reduce /
-   VJP pass instead of streaming it as separate work items.  Process-wide, not thread-safe. */
+   VJP pass instead of streaming it as separate work items.  TEST / TUNING HOOK like dpde_set_fast_path: process-wide
+   atomics; the per-stream thread-safety of the compute entry points does not extend to changing these concurrently. */
 int dpde_set_tuning(int key, int value);
 
 /* Bytes of scratch the reduce pass needs (per-CTA partial sums + a ticket counter).  The caller zero-fills it

@@ -34,7 +34,8 @@ def main():
                "labels": torch.tensor([[0.2 + 0.05 * i, 0.3]])} for i in range(n_obs)]
     mask_a, mask_u = E.get_masks((H, W), 0.2, 0.2, 0.05, 0.05, generator=g)
     smp = dp.JointSampler(net, dev, (H, W), 2, B, 1, dp.heat_loss2, {"dx": 1.0 / (H - 1)}, num_steps=N)
-    res = E.test_loop(smp, loader, 20.0, 0.5, 20.0, mask_a=mask_a, mask_u=mask_u, seed=100)      # uses the default group
+    res = E.test_loop(smp, loader, 20.0, 0.5, 20.0, mask_a=mask_a, mask_u=mask_u, seed=100, tf32=False,
+                      keep_on_device=True)      # uses the default group
     assert res["MAE"].shape == (n_obs, 2, H, W) and res["denom_range"].shape == (n_obs, 2)
     if rank == 0:
         errs = {}

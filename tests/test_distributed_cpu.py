@@ -197,3 +197,17 @@ def _halo_job(rank, world):
 def test_dist_halo_exchange_and_row_gather_gloo(world):
     for ok, gathered_ok in _run(world, _halo_job):
         assert ok and gathered_ok
+
+
+def test_slab_sampler_rejects_unknown_transports():
+    """A typo such as 'nccl' must not fall through to a run without any halo exchange."""
+    from dynamical_pde_diffusion_b200.slab import SlabJointSampler
+
+    args = (torch.nn.Identity(), "cuda", (16, 8), 2, 1, 1, None, {})
+    for bad in ("nccl", "Peer", None, object()):
+        with pytest.raises(ValueError):
+            SlabJointSampler(*args, plan=SlabPlan(16, 2, 0), transport=bad)
+    with pytest.raises(ValueError):
+        SlabJointSampler(*args, plan=SlabPlan(16, 2, 0), transport="none")      # no exchange with two ranks
+    assert SlabJointSampler(*args, plan=SlabPlan(16, 1, 0), transport="none").transport_kind == "none"
+    assert SlabJointSampler(*args, plan=SlabPlan(16, 2, 1), transport="dist").transport_kind == "dist"

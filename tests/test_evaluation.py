@@ -120,7 +120,8 @@ def test_test_loop_matches_host_side_metrics(deterministic_fp32):
     smp = dp.JointSampler(net, dev, (H, W), 2, B, 1, dp.heat_loss2, {"dx": 1.0 / (H - 1)}, num_steps=N)
     logged = []
     torch.manual_seed(11)
-    res = E.test_loop(smp, loader, 20.0, 0.5, 20.0, mask_a=mask_a, mask_u=mask_u, max_num_samples=2, log=logged.append)
+    res = E.test_loop(smp, loader, 20.0, 0.5, 20.0, mask_a=mask_a, mask_u=mask_u, max_num_samples=2, log=logged.append,
+                      tf32=False, keep_on_device=True)
     assert res["MAE"].shape == (2, 2, H, W) and res["denom_range"].shape == (2, 2) and len(logged) == 2
     torch.manual_seed(11)                               # the same RNG stream -> the same latents per observation
     for i, batch in enumerate(loader[:2]):
@@ -133,5 +134,12 @@ def test_test_loop_matches_host_side_metrics(deterministic_fp32):
         np.testing.assert_allclose(res["std"][i], std.numpy(), rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(logged[i]["rel MAE"], float((mae / d_range[:, None, None]).mean()), rtol=1e-4)
     # default masks (model_testing.py:174-177): all-zero (C/2, H, W) -> observation losses are the constant-zero branch
-    res0 = E.test_loop(smp, loader, 20.0, 0.5, 20.0, max_num_samples=1)
+    res0 = E.test_loop(smp, loader, 20.0, 0.5, 20.0, max_num_samples=1, tf32=False, keep_on_device=True)
     assert np.isfinite(res0["MAE"]).all()
+    # defaults follow the reference's sampling_context (sample.py:622-637): TF32 convolutions while sampling, eval() mode,
+    # the net on the sampler's device during the loop and back on the CPU afterwards, precision setting restored
+    net.train()
+    before = torch.backends.cudnn.conv.fp32_precision
+    res1 = E.test_loop(smp, loader, 20.0, 0.5, 20.0, max_num_samples=1)
+    assert np.isfinite(res1["MAE"]).all() and not net.training
+    assert next(net.parameters()).device.type == "cpu" and torch.backends.cudnn.conv.fp32_precision == before
