@@ -23,8 +23,10 @@ EXPORTED = (
     "dpde_euler_predict_bwd", "dpde_heun_guided_update", "dpde_heun_guided_update_rows", "dpde_halo_pack", "dpde_halo_unpack",
     "dpde_set_fast_path", "dpde_peer_alloc", "dpde_peer_free", "dpde_peer_export", "dpde_peer_open", "dpde_peer_close",
     "dpde_halo_push", "dpde_flag_wait", "dpde_set_tuning", "dpde_heat_residual_sq_workspace_bytes", "dpde_heat_residual_sq",
-    "dpde_heat_residual_sq_vjp",
+    "dpde_heat_residual_sq_vjp", "dpde_guidance_reduce_post", "dpde_mailbox_wait_finalize", "dpde_heun_guided_update_rows_push",
 )
+ABI_VERSION = 2
+MAX_RANKS, MAILBOX_BYTES = 8, 512
 
 
 class View(C.Structure):
@@ -42,6 +44,18 @@ class GuidanceDesc(C.Structure):
         ("gamma", C.c_double), ("alpha", C.c_double), ("c_ex", C.c_double), ("c_an", C.c_double), ("tau", C.c_double),
         ("easy_axis", C.c_double * 3),
     ]
+
+
+class Mailbox(C.Structure):
+    """dpde_mailbox: cross-rank exchange of the three partial sums (boxes[r] = rank r's mailbox as mapped here)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint64), ("boxes", C.c_void_p * MAX_RANKS)]
+
+
+class HaloPeers(C.Structure):
+    """dpde_halo_peers: the neighbours' next-state buffers and flag words for the fused update + halo push."""
+    _fields_ = [("up64", C.c_void_p), ("up32", C.c_void_p), ("down64", C.c_void_p), ("down32", C.c_void_p),
+                ("flag_up", C.c_void_p), ("flag_down", C.c_void_p), ("ticket", C.c_void_p), ("epoch", C.c_uint64),
+                ("H_up", C.c_int32), ("H_down", C.c_int32)]
 
 
 class DpdeError(RuntimeError):
@@ -88,6 +102,9 @@ def lib():
     L.dpde_heat_residual_sq_workspace_bytes.restype = C.c_size_t
     L.dpde_heat_residual_sq.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp, dbl, vp, vp, vp]
     L.dpde_heat_residual_sq_vjp.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, vp, dbl, vp, vp, vp, vp]
+    L.dpde_guidance_reduce_post.argtypes = [C.POINTER(GuidanceDesc), vp, vp, C.POINTER(Mailbox), vp]
+    L.dpde_mailbox_wait_finalize.argtypes = [C.POINTER(GuidanceDesc), C.POINTER(Mailbox), dbl, vp, vp, vp, vp, vp]
+    L.dpde_heun_guided_update_rows_push.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, i64, i32, i32, i32, C.POINTER(HaloPeers), vp]
     for name in EXPORTED:
         fn = getattr(L, name)
         if name not in ("dpde_abi_version", "dpde_last_error", "dpde_guidance_workspace_bytes",

@@ -21,6 +21,7 @@
 // (SM count x occupancy) strides over tiles; consecutive lanes touch consecutive columns (coalesced 128 B rows).
 
 #include <atomic>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -43,7 +44,23 @@ struct Params {
     const double* coef;
     double inv_dx2, w_a, w_u, w_pde, hw;
     double gamma, alpha, c_ex, c_an, tau, e[3];
+    // cross-rank exchange of the partial sums (row slabs / coupled batch shards): mb_world > 0 makes the last CTA of a
+    // reduce pass post this rank's three sums into every rank's mailbox (peer stores + st.release.sys), see peer.cu
+    int mb_world, mb_rank;
+    unsigned long long mb_epoch;
+    void* mb_box[DPDE_MAX_RANKS];
 };
+
+// One mailbox = 2 parities x DPDE_MAX_RANKS source ranks x {sums[3], flag}: 32 bytes per slot
+struct MailSlot {
+    double s[3];
+    unsigned long long flag;
+};
+static_assert(sizeof(MailSlot) == 32 && 2 * DPDE_MAX_RANKS * sizeof(MailSlot) == DPDE_MAILBOX_BYTES, "mailbox layout");
+
+__device__ __forceinline__ MailSlot* mail_slot(void* box, unsigned long long epoch, int src) {
+    return reinterpret_cast<MailSlot*>(box) + (epoch & 1ull) * DPDE_MAX_RANKS + src;
+}
 
 struct TileCoord {
     int b, unit, y0, x0;
@@ -174,6 +191,56 @@ __device__ __forceinline__ void finalize_scalars(const Params& p, const double* 
     }
 }
 
+// ---- end of every reduce pass: deterministic CTA partial -> the last CTA (ticket counter) combines all partials in index
+//      order, optionally finalises the scalars, and -- fused compute + collective -- posts this rank's sums to every
+//      rank's mailbox over NVLink peer memory: thread r stores the three doubles into slot [epoch & 1][my rank] of rank
+//      r's mailbox and publishes them with st.release.sys on the slot's flag word.  dpde_mailbox_wait_finalize on each
+//      rank acquires the `world` flags and adds the slots in rank order, so every rank forms the same total.
+__device__ __forceinline__ void reduce_epilogue(const Params& p, double s_a, double s_u, double s_p, double* scratch, bool* is_last,
+                                                double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                double* __restrict__ sums, int finalize, double* __restrict__ scal,
+                                                float* __restrict__ trace) {
+    const int tid = threadIdx.x;
+    block_sum3(s_a, s_u, s_p, scratch);
+    if (tid == 0) {
+        partials[3 * blockIdx.x + 0] = s_a;
+        partials[3 * blockIdx.x + 1] = s_u;
+        partials[3 * blockIdx.x + 2] = s_p;
+        __threadfence();
+        *is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*is_last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
+        a += __ldcg(partials + 3 * i);
+        b += __ldcg(partials + 3 * i + 1);
+        c += __ldcg(partials + 3 * i + 2);
+    }
+    block_sum3(a, b, c, scratch);
+    if (tid == 0) {
+        sums[0] = a;
+        sums[1] = b;
+        sums[2] = c;
+        if (finalize) finalize_scalars(p, sums, scal, trace);
+        *ticket = 0u;
+        scratch[0] = a;
+        scratch[1] = b;
+        scratch[2] = c;
+    }
+    if (p.mb_world > 0) {
+        __syncthreads();
+        if (tid < p.mb_world) {
+            MailSlot* slot = mail_slot(p.mb_box[tid], p.mb_epoch, p.mb_rank);
+            slot->s[0] = scratch[0];
+            slot->s[1] = scratch[1];
+            slot->s[2] = scratch[2];
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&slot->flag), "l"(p.mb_epoch) : "memory");
+        }
+    }
+}
+
 // =========================================================================================================
 // pass 1: global sums
 // =========================================================================================================
@@ -269,37 +336,55 @@ guidance_reduce_kernel(const __grid_constant__ Params p, double* __restrict__ pa
         }
     }
 
-    // ---- CTA partial -> global, last CTA combines all partials in a fixed order (deterministic)
-    block_sum3(s_a, s_u, s_p, scratch);
-    if (tid == 0) {
-        partials[3 * blockIdx.x + 0] = s_a;
-        partials[3 * blockIdx.x + 1] = s_u;
-        partials[3 * blockIdx.x + 2] = s_p;
-        __threadfence();
-        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
-        a += __ldcg(partials + 3 * i);
-        b += __ldcg(partials + 3 * i + 1);
-        c += __ldcg(partials + 3 * i + 2);
-    }
-    block_sum3(a, b, c, scratch);
-    if (tid == 0) {
-        sums[0] = a;
-        sums[1] = b;
-        sums[2] = c;
-        if (finalize) finalize_scalars(p, sums, scal, trace);
-        *ticket = 0u;
-    }
+    reduce_epilogue(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
 __global__ void finalize_kernel(const __grid_constant__ Params p, const double* __restrict__ sums,
                                 double* __restrict__ scal, float* __restrict__ trace) {
     if (threadIdx.x == 0 && blockIdx.x == 0) finalize_scalars(p, sums, scal, trace);
+}
+
+// Other half of the mailbox exchange: one warp.  Lane r < world spins (ld.acquire.sys, bounded by a timeout) on the flag
+// of slot [epoch & 1][r] of THIS rank's mailbox, i.e. on rank r's post of the current step; the slots are then added in
+// rank order -- the same order on every rank, so all ranks finalise identical totals -- and the scalars are finalised.
+__global__ void mailbox_wait_finalize_kernel(const __grid_constant__ Params p, unsigned long long timeout_ns, int* __restrict__ status,
+                                             double* __restrict__ sums, double* __restrict__ scal, float* __restrict__ trace) {
+    const int lane = threadIdx.x;
+    double v[3] = {0.0, 0.0, 0.0};
+    bool ok = true;
+    if (lane < p.mb_world) {
+        const MailSlot* slot = mail_slot(p.mb_box[p.mb_rank], p.mb_epoch, lane);
+        unsigned long long t0, now, f;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&slot->flag) : "memory");
+            if (f >= p.mb_epoch) break;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) {
+                ok = false;
+                break;
+            }
+            __nanosleep(100);
+        }
+        if (ok) {
+            v[0] = slot->s[0];
+            v[1] = slot->s[1];
+            v[2] = slot->s[2];
+        }
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    double tot[3] = {0.0, 0.0, 0.0};
+    for (int r = 0; r < p.mb_world; ++r) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tot[k] += __shfl_sync(0xffffffffu, v[k], r);
+    }
+    if (lane == 0) {
+        if (!all_ok && status) *status = 1;
+        sums[0] = tot[0];
+        sums[1] = tot[1];
+        sums[2] = tot[2];
+        finalize_scalars(p, sums, scal, trace);
+    }
 }
 
 // =========================================================================================================
@@ -657,7 +742,8 @@ std::atomic<bool> g_fast_path{true};
 // experiment knobs (dpde_set_tuning): [0] strip layout 0 = per pass (reduce 120 columns + 1 halo lane, VJP 112 + 2,
 // sector aligned), 1 = 120 + 1 in both, 2 = 112 + 2 in both;
 // [1] unused; [2] rows per chunk (0 = automatic); [3] / [4] 1 = pair a-planes with u-planes in the
-// reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s)
+// reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s);
+// [5] 1 = interior work items take the general loops too (A/B runs of the lean interior loops)
 std::atomic<int> g_tuning[8] = {};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -688,6 +774,7 @@ bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
 
 MarchGeom march_geometry(const Params& p, bool vjp) {
     MarchGeom g;
+    g.lean = g_tuning[5] == 0;
     const int rows = p.yhi - p.ylo;
     if (p.W <= 128) {
         int lw = 1, l2 = 0;
@@ -710,6 +797,8 @@ MarchGeom march_geometry(const Params& p, bool vjp) {
     int R = vjp ? 128 : 64;
     while (R > 32 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < 2 * want_warps) R >>= 1;
     while (R > 4 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
+    // the VJP's lean interior loop runs R + 2 row iterations in groups of its ring depth (8): 126, 62, 30, 14
+    if (vjp && R >= 16) R -= 2;
     if (g_tuning[2] > 0) R = g_tuning[2];
     g.R = R;
     g.chunks = (rows + R - 1) / R;
@@ -966,6 +1055,8 @@ int validate_and_fill(const dpde_guidance_desc* d, int tile_pix, Params& p, cons
     if (d->has_u && (cu < 1 || !d->obs_u.ptr || !d->mask_u.ptr)) return fail(DPDE_ERR_INVALID, "%s: has_u without obs_u/mask_u", who);
 
     p.B = d->B; p.C = d->C; p.ch_a = d->ch_a; p.H = d->H; p.W = d->W; p.kind = d->pde_kind;
+    p.mb_world = 0; p.mb_rank = 0; p.mb_epoch = 0;
+    for (auto& b : p.mb_box) b = nullptr;
     if (d->slab_H_global > 0) {
         const int need = (d->pde_kind == DPDE_PDE_HEAT || d->pde_kind == DPDE_PDE_LLG_RESIDUAL) ? 2 : 0;
         if (d->slab_halo < need) return fail(DPDE_ERR_INVALID, "%s: slab_halo %d < %d needed by this residual", who, d->slab_halo, need);
@@ -1066,12 +1157,27 @@ int dpde_set_tuning(int key, int value) {
 
 size_t dpde_guidance_workspace_bytes(void) { return (size_t)(3 * kMaxPartials + 2) * sizeof(double); }
 
-int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize, double* scalars,
-                         float* trace_row, dpde_stream_t stream) {
+namespace {
+int fill_mailbox(const dpde_mailbox* mbox, Params& p, const char* who) {
+    if (!mbox) return fail(DPDE_ERR_INVALID, "%s: mailbox is NULL", who);
+    if (mbox->world < 1 || mbox->world > DPDE_MAX_RANKS || mbox->rank < 0 || mbox->rank >= mbox->world)
+        return fail(DPDE_ERR_INVALID, "%s: need 1 <= world <= %d and 0 <= rank < world", who, DPDE_MAX_RANKS);
+    if (mbox->epoch == 0) return fail(DPDE_ERR_INVALID, "%s: epoch must be >= 1 (mailboxes start zeroed)", who);
+    for (int r = 0; r < mbox->world; ++r)
+        if (!mbox->boxes[r]) return fail(DPDE_ERR_INVALID, "%s: boxes[%d] is NULL", who, r);
+    p.mb_world = mbox->world; p.mb_rank = mbox->rank; p.mb_epoch = mbox->epoch;
+    for (int r = 0; r < mbox->world; ++r) p.mb_box[r] = mbox->boxes[r];
+    return DPDE_OK;
+}
+
+int reduce_impl(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize, double* scalars, float* trace_row,
+                const dpde_mailbox* mbox, dpde_stream_t stream, const char* who) {
     Params p;
-    if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, "dpde_guidance_reduce")) return rc;
-    if (!workspace || !sums) return fail(DPDE_ERR_INVALID, "dpde_guidance_reduce: workspace/sums is NULL");
-    if (finalize && !scalars) return fail(DPDE_ERR_INVALID, "dpde_guidance_reduce: finalize needs scalars");
+    if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, who)) return rc;
+    if (!workspace || !sums) return fail(DPDE_ERR_INVALID, "%s: workspace/sums is NULL", who);
+    if (finalize && !scalars) return fail(DPDE_ERR_INVALID, "%s: finalize needs scalars", who);
+    if (mbox)
+        if (int rc = fill_mailbox(mbox, p, who)) return rc;
     double* partials = reinterpret_cast<double*>(workspace);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + 3 * kMaxPartials);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1085,6 +1191,30 @@ int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double
     if (llg_eligible(p, nullptr, nullptr)) return launch_llg_reduce(p, partials, ticket, sums, finalize, scalars, trace_row, s);
     return p.x0.dtype == DPDE_F32 ? launch_reduce<float>(p, partials, ticket, sums, finalize, scalars, trace_row, s)
                                   : launch_reduce<double>(p, partials, ticket, sums, finalize, scalars, trace_row, s);
+}
+}  // namespace
+
+int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double* sums, int finalize, double* scalars,
+                         float* trace_row, dpde_stream_t stream) {
+    return reduce_impl(desc, workspace, sums, finalize, scalars, trace_row, nullptr, stream, "dpde_guidance_reduce");
+}
+
+int dpde_guidance_reduce_post(const dpde_guidance_desc* desc, void* workspace, double* sums, const dpde_mailbox* mbox,
+                              dpde_stream_t stream) {
+    if (!mbox) return fail(DPDE_ERR_INVALID, "dpde_guidance_reduce_post: mailbox is NULL");
+    return reduce_impl(desc, workspace, sums, 0, nullptr, nullptr, mbox, stream, "dpde_guidance_reduce_post");
+}
+
+int dpde_mailbox_wait_finalize(const dpde_guidance_desc* desc, const dpde_mailbox* mbox, double timeout_s, int32_t* status,
+                               double* sums, double* scalars, float* trace_row, dpde_stream_t stream) {
+    const char* who = "dpde_mailbox_wait_finalize";
+    Params p;
+    if (int rc = validate_and_fill(desc, desc ? tile_pix_for(desc->pde_kind) : kTileHeat, p, who)) return rc;
+    if (!sums || !scalars) return fail(DPDE_ERR_INVALID, "%s: sums/scalars is NULL", who);
+    if (!(timeout_s > 0.0)) return fail(DPDE_ERR_INVALID, "%s: timeout_s must be > 0", who);
+    if (int rc = fill_mailbox(mbox, p, who)) return rc;
+    mailbox_wait_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, (unsigned long long)(timeout_s * 1e9), status, sums, scalars, trace_row);
+    return check_launch(who);
 }
 
 int dpde_guidance_finalize(const dpde_guidance_desc* desc, const double* sums, double* scalars, float* trace_row,

@@ -33,6 +33,7 @@ struct MarchGeom {
     int a_blocks_per_plane, n_a_items;   // a-plane work: blocks of kABlock float4 within one plane's owned rows
     int a_plane4;                        // float4 per a-plane (owned rows)
     int a_block4;                        // float4 per a-plane work item (kABlock, smaller on small problems)
+    int lean;                            // 1: interior work items take the lean loops (0 only via dpde_set_tuning, for A/B runs)
 };
 
 constexpr int kABlock = 1024;            // largest a-plane work item, in float4 (4096 pixels)
@@ -73,6 +74,45 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // exact uint8 -> double without the (quarter-rate) I2F.F64: 2^52 + k has k in its low mantissa bits
 __device__ __forceinline__ double u8_to_double(unsigned k) { return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0; }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Lean loops for INTERIOR work items (round 2).  ncu of the round-1 kernels: 145 instructions per row iteration in the
+// reduce pass of which only 44 were fp64 arithmetic and 12 conversions -- the rest was address arithmetic (four 64-bit
+// addresses rebuilt from constant-bank pointers per row), dynamic ring-slot indexing, the reflect / clamp row loader,
+// edge selects, mask widening (uint8 -> fp64 + multiply) and per-row validity flags; issue slots, not DRAM, were the
+// limit (65 % issue-active at 0.72 of the HBM peak).  An item is INTERIOR when every row it touches lies inside the
+// grid and the buffer, it is a full chunk, and no lane of the warp sits on a grid edge column -- all but the first /
+// last chunk of a plane and the two edge strips.  For those:
+//   * ring slots are compile-time (the loop is unrolled by exactly the ring depth), so every LDS / LDGSTS shared
+//     address is base + immediate;
+//   * four running 64-bit row pointers advance once per group of RD rows; the copy addresses inside a group are
+//     pointer + j * W (one IMAD.WIDE each);
+//   * no reflection, no clamps, no edge selects, no per-row validity: halo lanes accumulate into item-local sums that
+//     are dropped at the end of the item;
+//   * masks are 0 / 1 (the C ABI's DPDE_U8 operands are bool masks): the observation term is a predicated DFMA
+//     instead of widen + multiply + square.
+// Everything else (first / last chunks, edge strips, narrow grids, per-sample mode with g_dxdt, paired a-planes) runs
+// the general loops below, unchanged.
+// ---------------------------------------------------------------------------------------------------------
+template <int J>
+using IC = std::integral_constant<int, J>;
+
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(IC<N - 1>{});
+    }
+}
+
+// acc = fma(a, b, acc) where byte I of the mask word k is set (mask bytes are 0 / 1): a test + a PREDICATED DFMA -- the
+// C++ form `if (bit) acc = fma(...)` compiles to an unconditional DFMA and two FSELs
+template <int I>
+__device__ __forceinline__ void fma_if(double& acc, double a, double b, unsigned k) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}"
+        : "+d"(acc) : "d"(a), "d"(b), "r"(k), "n"(1u << (8 * I)));
+}
 
 struct D4v {
     double v[4];
@@ -220,6 +260,72 @@ __device__ __forceinline__ AItem a_decode(const Params& p, const MarchGeom& g, i
     return a;
 }
 
+// ---- a-plane streaming items (sum (mask (a - obs))^2 and its gradient), shared by the heat and LLG kernels ---------
+// Masks are 0 / 1, so an unobserved pixel is handled by selecting the OBSERVATION operand at 32 bits before it is
+// widened: o' = mask ? obs : a makes the difference exactly zero -- one FSEL instead of widening the mask to fp64 and
+// multiplying (the round-1 form cost 49 instructions per float4 in the reduce pass; this one ~30).
+__device__ __forceinline__ float sel_obs(unsigned m, float o, float v) { return m ? o : v; }
+
+__device__ __forceinline__ void a_item_reduce(const Params& p, const MarchGeom& g, int item, int lane, double& s_a) {
+    const AItem a = a_decode(p, g, item);
+    const int base = p.ylo * p.W + 4 * a.first4;
+    const float* pa = reinterpret_cast<const float*>(p.x0.p) + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
+    const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
+    const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
+    double s0 = 0.0, s1 = 0.0;
+    auto body = [&](int i) {
+        const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
+        const unsigned k = __ldg(reinterpret_cast<const unsigned*>(pm + 4 * i));
+        const double d0 = (double)v.x - (double)sel_obs(k & 0xffu, o.x, v.x), d1 = (double)v.y - (double)sel_obs(k & 0xff00u, o.y, v.y);
+        const double d2 = (double)v.z - (double)sel_obs(k & 0xff0000u, o.z, v.z), d3 = (double)v.w - (double)sel_obs(k & 0xff000000u, o.w, v.w);
+        s0 = fma(d0, d0, s0);
+        s1 = fma(d1, d1, s1);
+        s0 = fma(d2, d2, s0);
+        s1 = fma(d3, d3, s1);
+    };
+    int i0 = 0;
+    for (; i0 + 256 <= a.n4; i0 += 256) {   // full blocks: eight independent 128-bit loads per array at constant offsets
+#pragma unroll
+        for (int t = 0; t < 8; ++t) body(i0 + 32 * t + lane);
+    }
+    for (int i = i0 + lane; i < a.n4; i += 32) body(i);
+    s_a += s0 + s1;
+}
+
+__device__ __forceinline__ void a_item_vjp(const Params& p, const MarchGeom& g, int item, int lane, double c_a,
+                                           float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    const AItem a = a_decode(p, g, item);
+    const int base = p.ylo * p.W + 4 * a.first4;
+    const int64_t plane = (int64_t)p.H * p.W;
+    float* pg = g_x0 + ((int64_t)a.b * p.C + a.ch) * plane + base;
+    float* pgd = g_dxdt ? g_dxdt + ((int64_t)a.b * p.C + a.ch) * plane + base : nullptr;
+    if (p.has_a) {   // g = c_a mask (mask (a - obs)); zeros when the mask is empty (sample.py:337-342)
+        const float* pa = reinterpret_cast<const float*>(p.x0.p) + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
+        const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
+        const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
+        auto body = [&](int i) {
+            const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
+            const unsigned k = __ldg(reinterpret_cast<const unsigned*>(pm + 4 * i));
+            float4 w;
+            w.x = (float)(c_a * ((double)v.x - (double)sel_obs(k & 0xffu, o.x, v.x)));
+            w.y = (float)(c_a * ((double)v.y - (double)sel_obs(k & 0xff00u, o.y, v.y)));
+            w.z = (float)(c_a * ((double)v.z - (double)sel_obs(k & 0xff0000u, o.z, v.z)));
+            w.w = (float)(c_a * ((double)v.w - (double)sel_obs(k & 0xff000000u, o.w, v.w)));
+            *reinterpret_cast<float4*>(pg + 4 * i) = w;
+        };
+        int i0 = 0;
+        for (; i0 + 256 <= a.n4; i0 += 256) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) body(i0 + 32 * t + lane);
+        }
+        for (int i = i0 + lane; i < a.n4; i += 32) body(i);
+    } else {
+        for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pg + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (pgd)
+        for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pgd + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Each warp owns every nwarps-th u-item (compute/issue bound) and a-item (pure streaming, latency bound) and
 // alternates between the two kinds in proportion, odd warps starting with the other kind, so that at any time an
 // SM runs a mix of both and the streaming warps' memory stalls overlap the marching warps' arithmetic.
@@ -244,6 +350,88 @@ __device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, 
 // ---------------------------------------------------------------------------------------------------------
 // pass 1 (fast): S_a, S_u, S_pde
 // ---------------------------------------------------------------------------------------------------------
+// Register hygiene (round 2): the kernel body holds only the work-item loop and the LEAN interior loop.  The general
+// u-item loop (reflecting loader, edge selects, per-row validity, paired a-planes) and the a-plane streaming items are
+// __noinline__ device functions with their own register allocation -- inlined next to the lean loop they pushed the
+// 80-register reduce kernel into local-memory spills inside BOTH loops (measured: 0.394 ms instead of 0.336 ms).
+struct Sums3 {
+    double a, u, p;
+};
+
+// Is every row of [first, last] inside the local buffer and inside the global grid (no reflection, no clamp)?
+__device__ __forceinline__ bool rows_inside(const Params& p, int first, int last) {
+    return first >= 0 && last <= p.H - 1 && first + p.yg0 >= 0 && last + p.yg0 <= p.Hg - 1;
+}
+
+// General u-item of the reduce pass (any geometry).  Returns the item's contributions; in per-sample mode (PS) the
+// caller writes .p to partials.  Iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j],
+// uc = u[j+1]; ring element s is row ys + s: uc comes from element it+1, dudt / obs / mask from element it.
+template <bool HAS_D, bool HAS_O, int PA>
+__device__ __noinline__ Sums3 march_reduce_general(const Params& p, const MarchGeom& g, int wi, unsigned char* ring_mem) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int LW = 1 << g.lw_log2;
+    RowRing<HAS_D, HAS_O, PA, false> ring;
+    constexpr int kRing = ring_depth(PA, false);
+    ring.init(ring_mem, tid);
+    const MarchLane m = march_decode(p, g, wi, lane);
+    ring.bind(p, m, reinterpret_cast<const float*>(p.x0.p), reinterpret_cast<const float*>(p.dxdt.p));
+    const int n_it = g.R, n_el = g.R + 1;
+    ring.begin_item(p, m.ys, n_el - 1);
+    const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
+    double s_a = 0.0, s_u = 0.0, s_p = 0.0;
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
+    D4v ua = widen(ring.direct_u(p, m.ys - 1)), ub = widen(ring.direct_u(p, m.ys));
+#pragma unroll 2
+    for (int it = 0; it < n_it; ++it) {
+        cp_async_wait<kRing - 2>();                          // elements <= it + 1 have landed
+        const D4v uc = widen(ring.get_u(it + 1));
+        const float4 dt = ring.get_d(it), o = ring.get_o(it);
+        unsigned k = ring.get_m(it);
+        float4 av, oav;
+        unsigned ka = 0u;
+        if (PA == 1) {
+            av = ring.get_a(it);
+            oav = ring.get_oa(it);
+            ka = ring.get_ma(it);
+        }
+        const int sn = it + kRing;                           // refill the slot just drained
+        ring.issue(p, sn, sn < n_el, sn < n_it, sn < n_it);
+        double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
+        if (m.left_edge) lf = ub.v[1];                       // reflect: u[-1] = u[1]
+        if (m.right_edge) rt = ub.v[2];
+        const bool ok = m.out_ok && m.ys + it < m.ye;
+        double s[4];
+        lap_row(ua, ub, uc, lf, rt, s);
+        const double r0 = (double)dt.x - a_s * s[0], r1 = (double)dt.y - a_s * s[1];
+        const double r2 = (double)dt.z - a_s * s[2], r3 = (double)dt.w - a_s * s[3];
+        const double okf = ok ? 1.0 : 0.0;
+        s_p += okf * ((r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3));
+        if (HAS_O) {
+            if (!ok) k = 0u;
+            const double d0 = u8_to_double(k & 255u) * (ub.v[0] - (double)o.x), d1 = u8_to_double((k >> 8) & 255u) * (ub.v[1] - (double)o.y);
+            const double d2 = u8_to_double((k >> 16) & 255u) * (ub.v[2] - (double)o.z), d3 = u8_to_double(k >> 24) * (ub.v[3] - (double)o.w);
+            s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+        if (PA == 1) {   // paired a-plane row: sum (mask (a - obs))^2
+            if (!ok) ka = 0u;
+            const double d0 = u8_to_double(ka & 255u) * ((double)av.x - (double)oav.x), d1 = u8_to_double((ka >> 8) & 255u) * ((double)av.y - (double)oav.y);
+            const double d2 = u8_to_double((ka >> 16) & 255u) * ((double)av.z - (double)oav.z), d3 = u8_to_double(ka >> 24) * ((double)av.w - (double)oav.w);
+            s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+        ua = ub;
+        ub = uc;
+    }
+    cp_async_wait<0>();
+    return Sums3{s_a, s_u, s_p};
+}
+
+__device__ __noinline__ double a_item_reduce_call(const Params& p, const MarchGeom& g, int item) {
+    double s_a = 0.0;
+    a_item_reduce(p, g, item, threadIdx.x & 31, s_a);
+    return s_a;
+}
+
 // PS (per-sample mode, training loss models/loss.py:143): no global sums -- every row-segment item writes its own
 // sum of squared residuals to partials[item] (items of sample b are b, b + B, b + 2 B, ...: per_sample_items_kernel adds
 // them in that order), nothing else is touched.
@@ -256,125 +444,237 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     __shared__ double scratch[3 * (kThreads / 32)];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31;
-    const float* x0 = reinterpret_cast<const float*>(p.x0.p);
-    const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
-
-    // ---- a-planes: sum (mask (a - obs))^2; a warp streams one block of a plane with 128-bit loads
-    auto do_a = [&](int item) {
-        const AItem a = a_decode(p, g, item);
-        const int base = p.ylo * p.W + 4 * a.first4;
-        const float* pa = x0 + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
-        const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
-        const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
-#pragma unroll 8
-        for (int i = lane; i < a.n4; i += 32) {
-            const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
-            const uchar4 m = ldg4(pm + 4 * i);
-            const double d0 = u8_to_double(m.x) * ((double)v.x - (double)o.x), d1 = u8_to_double(m.y) * ((double)v.y - (double)o.y);
-            const double d2 = u8_to_double(m.z) * ((double)v.z - (double)o.z), d3 = u8_to_double(m.w) * ((double)v.w - (double)o.w);
-            s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        }
-    };
-
-    // ---- u-planes: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1].
-    //      Ring element s is row ys + s:  uc comes from element it+1, dudt / obs / mask from element it.
-    const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O, PA, false> ring;
+    using R_ = RowRing<HAS_D, HAS_O, 0, false>;
     constexpr int kRing = ring_depth(PA, false);
-    ring.init(ring_mem, tid);
+    constexpr unsigned F16 = kRing * kThreads * 16;
+    const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;   // RowRing::init's layout
+    const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
+
+    auto do_a = [&](int item) { s_a += a_item_reduce_call(p, g, item); };
+
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
-        ring.bind(p, m, x0, dxp);
-        const int n_it = g.R, n_el = g.R + 1;
-        ring.begin_item(p, m.ys, n_el - 1);
-#pragma unroll
-        for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
-        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
-        D4v ua = widen(ring.direct_u(p, m.ys - 1)), ub = widen(ring.direct_u(p, m.ys));
-#pragma unroll 3
-        for (int it = 0; it < n_it; ++it) {
-            cp_async_wait<kRing - 2>();                          // elements <= it + 1 have landed
-            const D4v uc = widen(ring.get_u(it + 1));
-            const float4 dt = ring.get_d(it), o = ring.get_o(it);
-            unsigned k = ring.get_m(it);
-            float4 av, oav;
-            unsigned ka = 0u;
-            if (PA == 1) {
-                av = ring.get_a(it);
-                oav = ring.get_oa(it);
-                ka = ring.get_ma(it);
-            }
-            const int sn = it + kRing;                           // refill the slot just drained
-            ring.issue(p, sn, sn < n_el, sn < n_it, sn < n_it);
-            double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
-            if (m.left_edge) lf = ub.v[1];                       // reflect: u[-1] = u[1]
-            if (m.right_edge) rt = ub.v[2];
-            const bool ok = m.out_ok && m.ys + it < m.ye;
-            double s[4];
-            lap_row(ua, ub, uc, lf, rt, s);
-            const double r0 = (double)dt.x - a_s * s[0], r1 = (double)dt.y - a_s * s[1];
-            const double r2 = (double)dt.z - a_s * s[2], r3 = (double)dt.w - a_s * s[3];
-            const double okf = ok ? 1.0 : 0.0;
-            s_p += okf * ((r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3));
-            if (HAS_O) {
-                if (!ok) k = 0u;
-                const double d0 = u8_to_double(k & 255u) * (ub.v[0] - (double)o.x), d1 = u8_to_double((k >> 8) & 255u) * (ub.v[1] - (double)o.y);
-                const double d2 = u8_to_double((k >> 16) & 255u) * (ub.v[2] - (double)o.z), d3 = u8_to_double(k >> 24) * (ub.v[3] - (double)o.w);
-                s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-            }
-            if (PA == 1) {   // paired a-plane row: sum (mask (a - obs))^2
-                if (!ok) ka = 0u;
-                const double d0 = u8_to_double(ka & 255u) * ((double)av.x - (double)oav.x), d1 = u8_to_double((ka >> 8) & 255u) * ((double)av.y - (double)oav.y);
-                const double d2 = u8_to_double((ka >> 16) & 255u) * ((double)av.z - (double)oav.z), d3 = u8_to_double(ka >> 24) * ((double)av.w - (double)oav.w);
-                s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-            }
-            ua = ub;
-            ub = uc;
+        const int n_it = g.R;
+        // interior item (see the note above static_for): full chunk, every row ys-1 .. ys+R inside grid and buffer, no
+        // lane on an edge column, chunk length a multiple of the ring depth.  One unconditional vote by all 32 lanes:
+        // lanes of different row segments may disagree on the per-lane part.
+        const bool interior = __all_sync(0xffffffffu, PA == 0 && g.lean && (n_it & (kRing - 1)) == 0 && m.ye - m.ys == n_it &&
+                                                          rows_inside(p, m.ys - 1, m.ys + n_it) && m.lane_ok && !m.left_edge && !m.right_edge);
+        double item_p;
+        if (interior) {
+            const int W = p.W;
+            const int ch = p.ch_a + m.cu;
+            // running row pointers (lane's column included): ring element 0 = row ys
+            const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + m.col0 + (int64_t)m.ys * W;
+            const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + m.col0 + (int64_t)m.ys * W : nullptr;
+            const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + m.col0 + (int64_t)m.ys * W : nullptr;
+            const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + m.col0 + (int64_t)m.ys * W : nullptr;
+            const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
+            D4v ua = widen(ldg4(pu - W)), ub = widen(ldg4(pu));
+            static_for<kRing>([&](auto J) {                               // prologue: elements 0 .. RD-1 (u of element 0 is ub)
+                constexpr int j = decltype(J)::value;
+                if (j >= 1) cp_async16(su + R_::slot16(j), pu + j * W);
+                if (HAS_D) cp_async16(sd + R_::slot16(j), pd + j * W);
+                if (HAS_O) {
+                    cp_async16(so + R_::slot16(j), po + j * W);
+                    cp_async4(sm + R_::slot4(j), pm + j * W);
+                }
+                cp_async_commit();
+            });
+            double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
+            auto group = [&](auto TAIL) {                                 // RD row iterations; refills elements e0 + RD + j
+                constexpr bool tail = decltype(TAIL)::value;
+                pu += kRing * W;
+                if (HAS_D) pd += kRing * W;
+                if (HAS_O) { po += kRing * W; pm += kRing * W; }
+                static_for<kRing>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    cp_async_wait<kRing - 2>();                           // elements <= it + 1 have landed
+                    const D4v uc = widen(lds128(su + R_::slot16(j + 1)));
+                    const float4 dt = HAS_D ? lds128(sd + R_::slot16(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned k = 0u;
+                    if (HAS_O) {
+                        o = lds128(so + R_::slot16(j));
+                        k = lds32(sm + R_::slot4(j));
+                    }
+                    if (!tail) {                                          // element it + RD -> the slot just drained
+                        cp_async16(su + R_::slot16(j), pu + j * W);
+                        if (HAS_D) cp_async16(sd + R_::slot16(j), pd + j * W);
+                        if (HAS_O) {
+                            cp_async16(so + R_::slot16(j), po + j * W);
+                            cp_async4(sm + R_::slot4(j), pm + j * W);
+                        }
+                    } else if (j == 0) {                                  // last group: only u of element n_it is still needed
+                        cp_async16(su + R_::slot16(j), pu + j * W);
+                    }
+                    cp_async_commit();
+                    const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
+                    double sv[4];
+                    lap_row(ua, ub, uc, lf, rt, sv);
+                    const double r0 = (double)dt.x - a_s * sv[0], r1 = (double)dt.y - a_s * sv[1];
+                    const double r2 = (double)dt.z - a_s * sv[2], r3 = (double)dt.w - a_s * sv[3];
+                    sp0 = fma(r0, r0, sp0);
+                    sp1 = fma(r1, r1, sp1);
+                    sp0 = fma(r2, r2, sp0);
+                    sp1 = fma(r3, r3, sp1);
+                    if (HAS_O) {                                          // mask in {0, 1}: (mask (u - obs))^2 = mask ? (u - obs)^2 : 0
+                        const double d0 = ub.v[0] - (double)o.x, d1 = ub.v[1] - (double)o.y;
+                        const double d2 = ub.v[2] - (double)o.z, d3 = ub.v[3] - (double)o.w;
+                        fma_if<0>(su0, d0, d0, k);
+                        fma_if<1>(su1, d1, d1, k);
+                        fma_if<2>(su0, d2, d2, k);
+                        fma_if<3>(su1, d3, d3, k);
+                    }
+                    ua = ub;
+                    ub = uc;
+                });
+            };
+            const int groups = n_it / kRing;
+#pragma unroll 1
+            for (int gi = 0; gi < groups - 1; ++gi) group(std::false_type{});
+            group(std::true_type{});
+            cp_async_wait<0>();
+            item_p = m.out_ok ? sp0 + sp1 : 0.0;                          // halo lanes computed on neighbouring columns: dropped here
+            if (m.out_ok) s_u += su0 + su1;
+        } else {
+            const Sums3 r = march_reduce_general<HAS_D, HAS_O, PA>(p, g, wi, ring_mem);
+            s_a += r.a;
+            s_u += r.u;
+            item_p = r.p;
         }
-        cp_async_wait<0>();
         if (PS) {   // segmented (LW-lane) butterfly, lane 0 of every segment owns the item's sum
-            double v = s_p;
+            const int LW = 1 << g.lw_log2;
+            double v = item_p;
             for (int o = LW >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LW);
             const unsigned si = (unsigned)wi * g.segs_per_warp + (lane >> g.lw_log2);
             if ((lane & (LW - 1)) == 0 && si < (unsigned)g.n_seg_items) partials[si] = v;
-            s_p = 0.0;
+        } else {
+            s_p += item_p;
         }
     };
     run_interleaved(warp0, nwarps, g.n_warp_items, (PA == 0 && p.has_a) ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
     if (PS) return;
 
-    block_sum3(s_a, s_u, s_p, scratch);
-    if (tid == 0) {
-        partials[3 * blockIdx.x + 0] = s_a;
-        partials[3 * blockIdx.x + 1] = s_u;
-        partials[3 * blockIdx.x + 2] = s_p;
-        __threadfence();
-        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
-        a += __ldcg(partials + 3 * i);
-        b += __ldcg(partials + 3 * i + 1);
-        c += __ldcg(partials + 3 * i + 2);
-    }
-    block_sum3(a, b, c, scratch);
-    if (tid == 0) {
-        sums[0] = a;
-        sums[1] = b;
-        sums[2] = c;
-        if (finalize) finalize_scalars(p, sums, scal, trace);
-        *ticket = 0u;
-    }
+    reduce_epilogue(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 (fast): seed gradient
 // ---------------------------------------------------------------------------------------------------------
+// General u-item of the VJP (any geometry).  Iteration `it` computes the residual of row j = ys - 1 + it (window
+// ua = u[j-1], ub = u[j], uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo],
+// r0 = r[jo+1].  Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
+template <bool HAS_D, bool HAS_O, int PA>
+__device__ __noinline__ void march_vjp_general(const Params& p, const MarchGeom& g, int wi, unsigned char* ring_mem, double c_a, double c_u,
+                                               double c_p, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int LW = 1 << g.lw_log2;
+    const int64_t plane = (int64_t)p.H * p.W;
+    RowRing<HAS_D, HAS_O, PA, true> ring;
+    constexpr int kRing = ring_depth(PA, true);
+    ring.init(ring_mem, tid);
+    const MarchLane m = march_decode(p, g, wi, lane);
+    ring.bind(p, m, reinterpret_cast<const float*>(p.x0.p), reinterpret_cast<const float*>(p.dxdt.p));
+    const int n_it = g.R + 2;
+    ring.begin_item(p, m.ys - 2, n_it + 1);
+    // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
+    const int ch = p.ch_a + m.cu, colc = ring.colc;
+    float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane;                                   // (+ colc at the store)
+    float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane : nullptr;
+    float* gaout = PA ? g_x0 + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;                 // paired a-plane
+    float* gadout = (PA && g_dxdt) ? g_dxdt + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;
+    const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
+    const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
+    D4v ua = widen(ring.direct_u(p, m.ys - 2)), ub = widen(ring.direct_u(p, m.ys - 1));
+    double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+    for (int it = 0; it < n_it; ++it) {
+        const int j = m.ys - 1 + it;
+        cp_async_wait<kRing - 3>();                          // elements <= it + 2 have landed
+        const D4v uc = widen(ring.get_u(it + 2));
+        const float4 dt = ring.get_d(it + 1), o = ring.get_o(it);
+        const unsigned k = ring.get_m(it);
+        float4 av, oav;
+        unsigned ka = 0u;
+        if (PA == 1) {
+            av = ring.get_a(it);
+            oav = ring.get_oa(it);
+            ka = ring.get_ma(it);
+        }
+        const int sn = it + kRing;
+        ring.issue(p, sn, sn < n_it + 2, sn < n_it + 1, sn < n_it);
+        double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
+        if (m.left_edge) lf = ub.v[1];
+        if (m.right_edge) rt = ub.v[2];
+        // r of rows outside the grid and of idle lanes is garbage (finite: it is computed from real, clamped
+        // data); it is never consumed: the vertical weights below vanish for out-of-grid neighbours and the
+        // edge lanes zero their horizontal neighbour.
+        double s[4], r0[4];
+        lap_row(ua, ub, uc, lf, rt, s);
+        r0[0] = (double)dt.x - a_s * s[0];
+        r0[1] = (double)dt.y - a_s * s[1];
+        r0[2] = (double)dt.z - a_s * s[2];
+        r0[3] = (double)dt.w - a_s * s[3];
+
+        double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1, LW), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1, LW);
+        if (m.left_edge) l1 = 0.0;
+        if (m.right_edge) q1 = 0.0;
+        const int jo = j - 1;
+        if (it >= 2 && jo < m.ye && m.out_ok) {
+            const int gjo = jo + p.yg0;
+            // transposed-stencil weights of the rows above / below: 2 from a boundary row, 0 from outside
+            const double wu = gjo == 0 ? 0.0 : (gjo == 1 ? 2.0 : 1.0);
+            const double wd = gjo == p.Hg - 1 ? 0.0 : (gjo == p.Hg - 2 ? 2.0 : 1.0);
+            const double a0 = ((wu * r2[0] + wd * r0[0]) + (l1 + r1[1])) - 4.0 * r1[0];
+            const double a1 = ((wu * r2[1] + wd * r0[1]) + (wl1 * r1[0] + r1[2])) - 4.0 * r1[1];
+            const double a2 = ((wu * r2[2] + wd * r0[2]) + (r1[1] + wr2 * r1[3])) - 4.0 * r1[2];
+            const double a3 = ((wu * r2[3] + wd * r0[3]) + (r1[2] + q1)) - 4.0 * r1[3];
+            double v0 = kp * a0, v1 = kp * a1, v2 = kp * a2, v3 = kp * a3;
+            if (HAS_O) {   // ua is u[jo]
+                const double m0 = u8_to_double(k & 255u), m1 = u8_to_double((k >> 8) & 255u), m2 = u8_to_double((k >> 16) & 255u), m3 = u8_to_double(k >> 24);
+                v0 += c_u * (m0 * (m0 * (ua.v[0] - (double)o.x)));
+                v1 += c_u * (m1 * (m1 * (ua.v[1] - (double)o.y)));
+                v2 += c_u * (m2 * (m2 * (ua.v[2] - (double)o.z)));
+                v3 += c_u * (m3 * (m3 * (ua.v[3] - (double)o.w)));
+            }
+            *reinterpret_cast<float4*>((gout + (int64_t)jo * p.W) + colc) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+            if (gdout)
+                *reinterpret_cast<float4*>((gdout + (int64_t)jo * p.W) + colc) =
+                    make_float4((float)(c_p * r1[0]), (float)(c_p * r1[1]), (float)(c_p * r1[2]), (float)(c_p * r1[3]));
+            if (PA) {   // paired a-plane, row jo: g = c_a mask (mask (a - obs)); zeros when mask_a is empty
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (PA == 1) {
+                    const double m0 = u8_to_double(ka & 255u), m1 = u8_to_double((ka >> 8) & 255u), m2 = u8_to_double((ka >> 16) & 255u), m3 = u8_to_double(ka >> 24);
+                    w.x = (float)(c_a * (m0 * (m0 * ((double)av.x - (double)oav.x))));
+                    w.y = (float)(c_a * (m1 * (m1 * ((double)av.y - (double)oav.y))));
+                    w.z = (float)(c_a * (m2 * (m2 * ((double)av.z - (double)oav.z))));
+                    w.w = (float)(c_a * (m3 * (m3 * ((double)av.w - (double)oav.w))));
+                }
+                *reinterpret_cast<float4*>((gaout + (int64_t)jo * p.W) + colc) = w;
+                if (gadout) *reinterpret_cast<float4*>((gadout + (int64_t)jo * p.W) + colc) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r2[i] = r1[i];
+            r1[i] = r0[i];
+        }
+        ua = ub;
+        ub = uc;
+    }
+    cp_async_wait<0>();
+}
+
+__device__ __noinline__ void a_item_vjp_call(const Params& p, const MarchGeom& g, int item, double c_a, float* __restrict__ g_x0,
+                                             float* __restrict__ g_dxdt) {
+    a_item_vjp(p, g, item, threadIdx.x & 31, c_a, g_x0, g_dxdt);
+}
+
 // PS (per-sample mode): `upstream` holds one seed per sample, c_p of an item = 2 upstream[b] (d r^2 / d r), no
 // observation terms, `scal` is not read.
 template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
@@ -385,141 +685,115 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     const int tid = threadIdx.x, lane = tid & 31;
     const double up = (!PS && upstream) ? __ldg(upstream) : 1.0;
     const double c_a = PS ? 0.0 : __ldg(scal + 4) * up, c_u = PS ? 0.0 : __ldg(scal + 5) * up;
-    double c_p = PS ? 0.0 : __ldg(scal + 6) * up;
-    const float* x0 = reinterpret_cast<const float*>(p.x0.p);
-    const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
-    const int64_t plane = (int64_t)p.H * p.W;
+    const double c_p0 = PS ? 0.0 : __ldg(scal + 6) * up;
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
-
-    // ---- a-planes: g = c_a mask (mask (a - obs)), zeros when the mask is empty (sample.py:337-342)
-    auto do_a = [&](int item) {
-        const AItem a = a_decode(p, g, item);
-        const int base = p.ylo * p.W + 4 * a.first4;
-        float* pg = g_x0 + ((int64_t)a.b * p.C + a.ch) * plane + base;
-        float* pgd = g_dxdt ? g_dxdt + ((int64_t)a.b * p.C + a.ch) * plane + base : nullptr;
-        if (p.has_a) {
-            const float* pa = x0 + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
-            const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
-            const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
-#pragma unroll 8
-            for (int i = lane; i < a.n4; i += 32) {
-                const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
-                const uchar4 m = ldg4(pm + 4 * i);
-                const double m0 = u8_to_double(m.x), m1 = u8_to_double(m.y), m2 = u8_to_double(m.z), m3 = u8_to_double(m.w);
-                float4 w;
-                w.x = (float)(c_a * (m0 * (m0 * ((double)v.x - (double)o.x))));
-                w.y = (float)(c_a * (m1 * (m1 * ((double)v.y - (double)o.y))));
-                w.z = (float)(c_a * (m2 * (m2 * ((double)v.z - (double)o.z))));
-                w.w = (float)(c_a * (m3 * (m3 * ((double)v.w - (double)o.w))));
-                *reinterpret_cast<float4*>(pg + 4 * i) = w;
-            }
-        } else {
-            for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pg + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (pgd)
-            for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pgd + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-
-    // ---- u-planes.  Iteration `it` computes the residual of row j = ys - 1 + it (window ua = u[j-1], ub = u[j],
-    //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
-    //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
-    const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O, PA, true> ring;
+    using R_ = RowRing<HAS_D, HAS_O, 0, true>;
     constexpr int kRing = ring_depth(PA, true);
-    ring.init(ring_mem, tid);
+    constexpr unsigned F16 = kRing * kThreads * 16;
+    const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;   // RowRing::init's layout
+    const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
+
+    auto do_a = [&](int item) { a_item_vjp_call(p, g, item, c_a, g_x0, g_dxdt); };
+
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
-        ring.bind(p, m, x0, dxp);
         const int n_it = g.R + 2;
-        ring.begin_item(p, m.ys - 2, n_it + 1);
-        // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
-#pragma unroll
-        for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
-        const int ch = p.ch_a + m.cu, colc = ring.colc;
-        float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane;                                   // (+ colc at the store)
-        float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane : nullptr;
-        float* gaout = PA ? g_x0 + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;                 // paired a-plane
-        float* gadout = (PA && g_dxdt) ? g_dxdt + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;
-        if (PS) c_p = 2.0 * __ldg(upstream + m.b);
-        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
-        const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
-        D4v ua = widen(ring.direct_u(p, m.ys - 2)), ub = widen(ring.direct_u(p, m.ys - 1));
-        double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 3
-        for (int it = 0; it < n_it; ++it) {
-            const int j = m.ys - 1 + it;
-            cp_async_wait<kRing - 3>();                          // elements <= it + 2 have landed
-            const D4v uc = widen(ring.get_u(it + 2));
-            const float4 dt = ring.get_d(it + 1), o = ring.get_o(it);
-            const unsigned k = ring.get_m(it);
-            float4 av, oav;
-            unsigned ka = 0u;
-            if (PA == 1) {
-                av = ring.get_a(it);
-                oav = ring.get_oa(it);
-                ka = ring.get_ma(it);
-            }
-            const int sn = it + kRing;
-            ring.issue(p, sn, sn < n_it + 2, sn < n_it + 1, sn < n_it);
-            double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
-            if (m.left_edge) lf = ub.v[1];
-            if (m.right_edge) rt = ub.v[2];
-            // r of rows outside the grid and of idle lanes is garbage (finite: it is computed from real, clamped
-            // data); it is never consumed: the vertical weights below vanish for out-of-grid neighbours and the
-            // edge lanes zero their horizontal neighbour.
-            double s[4], r0[4];
-            lap_row(ua, ub, uc, lf, rt, s);
-            r0[0] = (double)dt.x - a_s * s[0];
-            r0[1] = (double)dt.y - a_s * s[1];
-            r0[2] = (double)dt.z - a_s * s[2];
-            r0[3] = (double)dt.w - a_s * s[3];
-
-            double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1, LW), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1, LW);
-            if (m.left_edge) l1 = 0.0;
-            if (m.right_edge) q1 = 0.0;
-            const int jo = j - 1;
-            if (it >= 2 && jo < m.ye && m.out_ok) {
-                const int gjo = jo + p.yg0;
-                // transposed-stencil weights of the rows above / below: 2 from a boundary row, 0 from outside
-                const double wu = gjo == 0 ? 0.0 : (gjo == 1 ? 2.0 : 1.0);
-                const double wd = gjo == p.Hg - 1 ? 0.0 : (gjo == p.Hg - 2 ? 2.0 : 1.0);
-                const double a0 = ((wu * r2[0] + wd * r0[0]) + (l1 + r1[1])) - 4.0 * r1[0];
-                const double a1 = ((wu * r2[1] + wd * r0[1]) + (wl1 * r1[0] + r1[2])) - 4.0 * r1[1];
-                const double a2 = ((wu * r2[2] + wd * r0[2]) + (r1[1] + wr2 * r1[3])) - 4.0 * r1[2];
-                const double a3 = ((wu * r2[3] + wd * r0[3]) + (r1[2] + q1)) - 4.0 * r1[3];
-                double v0 = kp * a0, v1 = kp * a1, v2 = kp * a2, v3 = kp * a3;
-                if (HAS_O) {   // ua is u[jo]
-                    const double m0 = u8_to_double(k & 255u), m1 = u8_to_double((k >> 8) & 255u), m2 = u8_to_double((k >> 16) & 255u), m3 = u8_to_double(k >> 24);
-                    v0 += c_u * (m0 * (m0 * (ua.v[0] - (double)o.x)));
-                    v1 += c_u * (m1 * (m1 * (ua.v[1] - (double)o.y)));
-                    v2 += c_u * (m2 * (m2 * (ua.v[2] - (double)o.z)));
-                    v3 += c_u * (m3 * (m3 * (ua.v[3] - (double)o.w)));
-                }
-                *reinterpret_cast<float4*>((gout + (int64_t)jo * p.W) + colc) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
-                if (gdout)
-                    *reinterpret_cast<float4*>((gdout + (int64_t)jo * p.W) + colc) =
-                        make_float4((float)(c_p * r1[0]), (float)(c_p * r1[1]), (float)(c_p * r1[2]), (float)(c_p * r1[3]));
-                if (PA) {   // paired a-plane, row jo: g = c_a mask (mask (a - obs)); zeros when mask_a is empty
-                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (PA == 1) {
-                        const double m0 = u8_to_double(ka & 255u), m1 = u8_to_double((ka >> 8) & 255u), m2 = u8_to_double((ka >> 16) & 255u), m3 = u8_to_double(ka >> 24);
-                        w.x = (float)(c_a * (m0 * (m0 * ((double)av.x - (double)oav.x))));
-                        w.y = (float)(c_a * (m1 * (m1 * ((double)av.y - (double)oav.y))));
-                        w.z = (float)(c_a * (m2 * (m2 * ((double)av.z - (double)oav.z))));
-                        w.w = (float)(c_a * (m3 * (m3 * ((double)av.w - (double)oav.w))));
-                    }
-                    *reinterpret_cast<float4*>((gaout + (int64_t)jo * p.W) + colc) = w;
-                    if (gadout) *reinterpret_cast<float4*>((gadout + (int64_t)jo * p.W) + colc) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                r2[i] = r1[i];
-                r1[i] = r0[i];
-            }
-            ua = ub;
-            ub = uc;
+        const double c_p = PS ? 2.0 * __ldg(upstream + m.b) : c_p0;
+        // interior item (see the note above static_for): full chunk whose rows ys-2 .. ys+R+1 all lie inside grid and
+        // buffer (so no output row is one of the four rows with boundary weights), no lane on an edge column, no
+        // g_dxdt output, R + 2 a multiple of the ring depth.  One unconditional vote by all 32 lanes.
+        const bool interior = __all_sync(0xffffffffu, PA == 0 && g.lean && (n_it & (kRing - 1)) == 0 && n_it >= 2 * kRing && m.ye - m.ys == g.R &&
+                                                          !g_dxdt && rows_inside(p, m.ys - 2, m.ys + g.R + 1) && m.lane_ok && !m.left_edge && !m.right_edge);
+        if (!interior) {
+            march_vjp_general<HAS_D, HAS_O, PA>(p, g, wi, ring_mem, c_a, c_u, c_p, g_x0, g_dxdt);
+            return;
         }
+        const int W = p.W;
+        const int ch = p.ch_a + m.cu;
+        const int64_t first = (int64_t)(m.ys - 2) * W + m.col0;           // ring element 0 = row ys - 2 (lane's column included)
+        const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + first;
+        const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + first : nullptr;
+        const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + first : nullptr;
+        const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + first : nullptr;
+        float* pg = g_x0 + ((int64_t)m.b * p.C + ch) * ((int64_t)p.H * W) + first;   // output row of iteration `it` is element it
+        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
+        D4v ua = widen(ldg4(pu)), ub = widen(ldg4(pu + W));
+        static_for<kRing>([&](auto J) {                               // prologue: u / obs of elements >= 2, dudt of elements >= 1
+            constexpr int j = decltype(J)::value;
+            if (j >= 2) cp_async16(su + R_::slot16(j), pu + j * W);
+            if (HAS_D && j >= 1) cp_async16(sd + R_::slot16(j), pd + j * W);
+            if (HAS_O && j >= 2) {
+                cp_async16(so + R_::slot16(j), po + j * W);
+                cp_async4(sm + R_::slot4(j), pm + j * W);
+            }
+            cp_async_commit();
+        });
+        double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
+        auto group = [&](auto TAIL, bool first_group) {
+            constexpr bool tail = decltype(TAIL)::value;
+            pu += kRing * W;
+            if (HAS_D) pd += kRing * W;
+            if (HAS_O) { po += kRing * W; pm += kRing * W; }
+            static_for<kRing>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                cp_async_wait<kRing - 3>();                           // elements <= it + 2 have landed
+                const D4v uc = widen(lds128(su + R_::slot16(j + 2)));
+                const float4 dt = HAS_D ? lds128(sd + R_::slot16(j + 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned k = 0u;
+                if (HAS_O) {
+                    o = lds128(so + R_::slot16(j));
+                    k = lds32(sm + R_::slot4(j));
+                }
+                if (!tail) {                                          // element it + RD -> the slot just drained
+                    cp_async16(su + R_::slot16(j), pu + j * W);
+                    if (HAS_D) cp_async16(sd + R_::slot16(j), pd + j * W);
+                    if (HAS_O) {
+                        cp_async16(so + R_::slot16(j), po + j * W);
+                        cp_async4(sm + R_::slot4(j), pm + j * W);
+                    }
+                } else {                                              // last group: u of elements n_it, n_it + 1; dudt of element n_it
+                    if (j <= 1) cp_async16(su + R_::slot16(j), pu + j * W);
+                    if (HAS_D && j == 0) cp_async16(sd + R_::slot16(j), pd + j * W);
+                }
+                cp_async_commit();
+                const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
+                double sv[4], r0[4];
+                lap_row(ua, ub, uc, lf, rt, sv);
+                r0[0] = (double)dt.x - a_s * sv[0];
+                r0[1] = (double)dt.y - a_s * sv[1];
+                r0[2] = (double)dt.z - a_s * sv[2];
+                r0[3] = (double)dt.w - a_s * sv[3];
+                const double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1);
+                if ((j >= 2 || !first_group) && m.out_ok) {          // rows ys - 2, ys - 1 belong to the previous chunk
+                    // K^T r on an interior row / column: all weights are 1
+                    double v0 = kp * (((r2[0] + r0[0]) + (l1 + r1[1])) - 4.0 * r1[0]);
+                    double v1 = kp * (((r2[1] + r0[1]) + (r1[0] + r1[2])) - 4.0 * r1[1]);
+                    double v2 = kp * (((r2[2] + r0[2]) + (r1[1] + r1[3])) - 4.0 * r1[2]);
+                    double v3 = kp * (((r2[3] + r0[3]) + (r1[2] + q1)) - 4.0 * r1[3]);
+                    if (HAS_O) {                                      // mask in {0, 1}: c_u mask^2 (u - obs); ua is u of the output row
+                        fma_if<0>(v0, c_u, ua.v[0] - (double)o.x, k);
+                        fma_if<1>(v1, c_u, ua.v[1] - (double)o.y, k);
+                        fma_if<2>(v2, c_u, ua.v[2] - (double)o.z, k);
+                        fma_if<3>(v3, c_u, ua.v[3] - (double)o.w, k);
+                    }
+                    *reinterpret_cast<float4*>(pg + j * W) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    r2[i] = r1[i];
+                    r1[i] = r0[i];
+                }
+                ua = ub;
+                ub = uc;
+            });
+            pg += kRing * W;
+        };
+        const int groups = n_it / kRing;
+        group(std::false_type{}, true);
+#pragma unroll 1
+        for (int gi = 1; gi < groups - 1; ++gi) group(std::false_type{}, false);
+        group(std::true_type{}, false);
         cp_async_wait<0>();
     };
     run_interleaved(warp0, nwarps, g.n_warp_items, PA == 0 ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);

@@ -220,86 +220,6 @@ __device__ __forceinline__ void llg_obs_pair(const unsigned char* __restrict__ a
     d1 = k1 * (x1v - (double)o.y);
 }
 
-// a-plane streaming items (sum (mask (a - obs))^2 and its gradient), shared by the LLG kernels
-__device__ __forceinline__ void a_item_reduce(const Params& p, const MarchGeom& g, int item, int lane, double& s_a) {
-    const AItem a = a_decode(p, g, item);
-    const int base = p.ylo * p.W + 4 * a.first4;
-    const float* pa = reinterpret_cast<const float*>(p.x0.p) + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
-    const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
-    const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
-#pragma unroll 4
-    for (int i = lane; i < a.n4; i += 32) {
-        const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
-        const uchar4 m = ldg4(pm + 4 * i);
-        const double d0 = u8_to_double(m.x) * ((double)v.x - (double)o.x), d1 = u8_to_double(m.y) * ((double)v.y - (double)o.y);
-        const double d2 = u8_to_double(m.z) * ((double)v.z - (double)o.z), d3 = u8_to_double(m.w) * ((double)v.w - (double)o.w);
-        s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-    }
-}
-
-__device__ __forceinline__ void a_item_vjp(const Params& p, const MarchGeom& g, int item, int lane, double c_a,
-                                           float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
-    const AItem a = a_decode(p, g, item);
-    const int base = p.ylo * p.W + 4 * a.first4;
-    const int64_t plane = (int64_t)p.H * p.W;
-    float* pg = g_x0 + ((int64_t)a.b * p.C + a.ch) * plane + base;
-    float* pgd = g_dxdt ? g_dxdt + ((int64_t)a.b * p.C + a.ch) * plane + base : nullptr;
-    if (p.has_a) {
-        const float* pa = reinterpret_cast<const float*>(p.x0.p) + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
-        const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
-        const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
-#pragma unroll 4
-        for (int i = lane; i < a.n4; i += 32) {
-            const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
-            const uchar4 m = ldg4(pm + 4 * i);
-            const double m0 = u8_to_double(m.x), m1 = u8_to_double(m.y), m2 = u8_to_double(m.z), m3 = u8_to_double(m.w);
-            float4 w;
-            w.x = (float)(c_a * (m0 * (m0 * ((double)v.x - (double)o.x))));
-            w.y = (float)(c_a * (m1 * (m1 * ((double)v.y - (double)o.y))));
-            w.z = (float)(c_a * (m2 * (m2 * ((double)v.z - (double)o.z))));
-            w.w = (float)(c_a * (m3 * (m3 * ((double)v.w - (double)o.w))));
-            *reinterpret_cast<float4*>(pg + 4 * i) = w;
-        }
-    } else {
-        for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pg + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (pgd)
-        for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pgd + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-// deterministic CTA partial -> last CTA combines in index order (same scheme as the other reduce kernels)
-__device__ __forceinline__ void reduce_epilogue(const Params& p, double s_a, double s_u, double s_p, double* scratch, bool* is_last,
-                                                double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                                double* __restrict__ sums, int finalize, double* __restrict__ scal,
-                                                float* __restrict__ trace) {
-    const int tid = threadIdx.x;
-    block_sum3(s_a, s_u, s_p, scratch);
-    if (tid == 0) {
-        partials[3 * blockIdx.x + 0] = s_a;
-        partials[3 * blockIdx.x + 1] = s_u;
-        partials[3 * blockIdx.x + 2] = s_p;
-        __threadfence();
-        *is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!*is_last) return;
-    __threadfence();
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
-        a += __ldcg(partials + 3 * i);
-        b += __ldcg(partials + 3 * i + 1);
-        c += __ldcg(partials + 3 * i + 2);
-    }
-    block_sum3(a, b, c, scratch);
-    if (tid == 0) {
-        sums[0] = a;
-        sums[1] = b;
-        sums[2] = c;
-        if (finalize) finalize_scalars(p, sums, scal, trace);
-        *ticket = 0u;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // m x H_eff residual, pass 1: S_a, S_u, S_pde
 //   Pipeline per CTA: while tile t is evaluated, the cp.async copies of tile t + grid (magnetisation rows and the

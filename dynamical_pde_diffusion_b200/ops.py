@@ -82,9 +82,9 @@ def broadcast_view(t: torch.Tensor, B: int, ch: int, H: int, W: int, kind: str) 
     (``model_testing.py:174-177``), (1,ch,H,W) observations (``model_testing.py:192-193``), full (B,ch,H,W).
     """
     if t.dtype == torch.bool:
-        t = t.to(torch.uint8)
-    elif t.dtype not in _DTYPES or (kind == "obs" and t.dtype == torch.uint8):
-        t = t.to(torch.float64)
+        t = t.view(torch.uint8)        # the C ABI's DPDE_U8 operands are 0 / 1 masks (the fast paths test bits, not values)
+    elif t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)        # weights of any other dtype (uint8 included) keep the reference's multiply semantics
     if t.shape[-2:] != (H, W):
         t = t.expand(*t.shape[:-2], H, W).contiguous() if t.dim() >= 2 else t.expand(H, W).contiguous()
     t = _rows_contiguous(t)
@@ -175,6 +175,18 @@ class GuidanceEngine:
         _ffi.call("dpde_guidance_reduce", C.byref(self.desc), self.workspace.data_ptr(), self.sums.data_ptr(), int(finalize),
                   self.scalars.data_ptr(), trace_row.data_ptr() if trace_row is not None else None, _stream())
         return keep
+
+    def reduce_post(self, x0, dxdt, weights, mailbox):
+        """Pass 1 fused with the first half of the cross-rank sum exchange: the reduce kernel's last CTA posts this
+        rank's sums into every rank's mailbox over peer memory (``dpde_guidance_reduce_post``)."""
+        keep = self._bind(x0, dxdt, weights)
+        _ffi.call("dpde_guidance_reduce_post", C.byref(self.desc), self.workspace.data_ptr(), self.sums.data_ptr(), C.byref(mailbox), _stream())
+        return keep
+
+    def wait_finalize(self, mailbox, timeout_s, status, trace_row=None):
+        """Second half: wait for every rank's post, add the slots in rank order into ``sums``, finalise the scalars."""
+        _ffi.call("dpde_mailbox_wait_finalize", C.byref(self.desc), C.byref(mailbox), float(timeout_s), status.data_ptr(),
+                  self.sums.data_ptr(), self.scalars.data_ptr(), trace_row.data_ptr() if trace_row is not None else None, _stream())
 
     def finalize(self, trace_row=None):
         _ffi.call("dpde_guidance_finalize", C.byref(self.desc), self.sums.data_ptr(), self.scalars.data_ptr(),

@@ -333,9 +333,17 @@ class JointSampler(Sampler):
         ctx = dict(x32=x32, stash=stash, x0_1c=x0_1c, xN=xN, dxdt=dxdt, dx_c=dx_c, want_d=want_d, w=w, last=last,
                    s_cur=s_cur, s_next=s_next)
         if r["fused"]:
-            engine.reduce(xN.detach(), dx_c, w, trace_row=r["trace"][i] if r["allreduce"] is None else None,
-                          finalize=r["allreduce"] is None)
+            self._pass1(r, engine, xN.detach(), dx_c, w, i)
         return ctx
+
+    # ---- the two halves of the sum reduction; multi-GPU subclasses (row slabs) replace them ----------------------
+    def _pass1(self, r, engine, xN, dx_c, w, i):
+        engine.reduce(xN, dx_c, w, trace_row=r["trace"][i] if r["allreduce"] is None else None, finalize=r["allreduce"] is None)
+
+    def _combine(self, r, engine, i):
+        if r["allreduce"] is not None:
+            r["allreduce"](engine.sums)
+            engine.finalize(r["trace"][i])
 
     def _step_back(self, ctx):
         """(all-reduce of the sums,) seed gradient, backward through the denoiser(s), fused Heun + guidance update."""
@@ -343,9 +351,7 @@ class JointSampler(Sampler):
         i, engine = r["i"], r["engine"]
         xN, dxdt, dx_c, want_d, w, last = ctx["xN"], ctx["dxdt"], ctx["dx_c"], ctx["want_d"], ctx["w"], ctx["last"]
         if r["fused"]:
-            if r["allreduce"] is not None:
-                r["allreduce"](engine.sums)
-                engine.finalize(r["trace"][i])
+            self._combine(r, engine, i)
             g, gd = engine.vjp(xN.detach(), dx_c, w, want_d)
         else:
             g, gd = self._seed_generic(engine, xN.detach(), dx_c, w, r["trace"][i], want_d, r["allreduce"])

@@ -5,15 +5,32 @@ Rank r owns global rows ``[r0, r1)`` of every (b, c) plane and keeps ``halo = 2`
 fused heat VJP needs (residual at +-1 row, its stencil another row) and what the LLG residual needs.  Reflect
 boundaries apply only at the global top and bottom (``slab_row0`` / ``slab_H_global`` of ``dpde_guidance_desc``).
 
-Per guided step and rank:
+Per guided step and rank (``transport="peer"``, the product path):
 
-    [dpde_flag_wait]                      ghost rows of the state pushed by the neighbours have landed
+    dpde_flag_wait                        ghost rows of the state pushed by the neighbours have landed (usually long ago)
     denoiser(s) + dpde_euler_predict      on the whole local buffer: a pointwise / local denoiser maps valid ghost
                                           rows of the state to valid ghost rows of x0-hat -- no exchange of x0-hat
-    dpde_guidance_reduce (owned rows)     partial sums  ->  all-reduce of 3 doubles  ->  dpde_guidance_finalize
+    dpde_guidance_reduce_post             partial sums of the owned rows; the kernel's last CTA stores them into EVERY
+                                          rank's mailbox through peer pointers and releases the slot's flag
+    dpde_mailbox_wait_finalize            acquires the `world` slots, adds them in rank order, finalises the scalars
     dpde_guidance_vjp   (owned rows)      seed gradient; torch.autograd through the denoiser
-    dpde_heun_guided_update_rows          writes the owned rows of the next state (fp64 + fp32 copy)
-    dpde_halo_push x2                     boundary rows -> neighbours' ghost rows over NVLink peer memory, then flags
+    dpde_heun_guided_update_rows_push     ONE kernel: the owned boundary rows are updated first and stored twice (local
+                                          next state + the neighbours' ghost rows over NVLink), the flags are released
+                                          as soon as those CTAs have fenced, the interior rows follow -- the transfer and
+                                          the neighbours' wake-up overlap the bulk of the update
+
+No NCCL call and no host synchronisation inside the loop.  ``transport="dist"`` keeps the library baseline
+(``torch.distributed`` all-reduce of the three sums + send/recv of the ghost rows; gloo in the CPU tests).
+
+Ordering (why nobody overwrites rows a neighbour is still reading).  The state ping-pongs between two buffers.  In
+step s a rank reads buffer p (ghost rows included) and writes the owned rows of buffer 1-p; its push lands in the
+NEIGHBOURS' ghost rows of buffer 1-p, which they last read in step s-1.  A rank's update of step s runs after its
+``wait_finalize`` of step s, i.e. after EVERY rank has posted its step-s sums -- and a rank posts them from the reduce
+kernel of step s, which its stream orders after all of its step s-1 kernels.  So every reader of the old contents is
+done before the first peer store of step s can happen.  The sum exchange is therefore not optional decoration: it is
+the synchronisation the halo push relies on (with ``dist`` the all-reduce plays the same role).  The mailbox slots are
+double-buffered by step parity for the same reason: a rank reaches exchange e + 2 only after every rank has finished
+reading exchange e.
 
 The denoiser must be *local* (its output at a row depends on the input within ``halo`` rows... in fact, with one
 state exchange per step, on the same row only): the reference U-Net cannot run at this size (activations exceed
@@ -151,15 +168,19 @@ def _align(n, a=256):
 
 
 class PeerHaloExchange:
-    """State buffers in exportable memory + the neighbours' mappings + the push / wait launches.
+    """State buffers in exportable memory + every rank's mapping + the per-step descriptors.
 
-    Layout of one rank's allocation: ``x64[0] | x64[1] | x32[0] | x32[1] | flags (8 x u64) | ticket | status``.
-    Flags: index 2 k + side, k = 0 fp64 state, 1 fp32 copy; side 0 = written by the upper neighbour, 1 = lower.
+    Layout of one rank's allocation: ``x64[0] | x64[1] | x32[0] | x32[1] | flags (8 x u64) | mailbox | ticket | status``.
+    Flags: index 2 k + side; side 0 = written by the upper neighbour, 1 = by the lower one.  The fused update + push
+    raises the k = 0 pair once per step; the stand-alone :meth:`push` (one field per launch) raises pair k per field.
+    Mailbox: ``DPDE_MAILBOX_BYTES`` -- 2 step parities x 8 source ranks x {sums[3], flag}.
     """
 
     N_FLAGS = 8
 
     def __init__(self, plan: SlabPlan, planes: int, W: int, device):
+        if plan.world > _ffi.MAX_RANKS:
+            raise ValueError(f"the peer-memory exchange supports up to {_ffi.MAX_RANKS} ranks (one NVSwitch domain), got {plan.world}")
         self.plan, self.planes, self.W, self.device = plan, planes, W, torch.device(device)
         self.elems = lambda Hl: planes * Hl * W
         self.offsets = self._offsets(plan.H_local)
@@ -168,16 +189,17 @@ class PeerHaloExchange:
         self.x64 = [self.buf.tensor(o["x64_0"], shape, F64, self.device), self.buf.tensor(o["x64_1"], shape, F64, self.device)]
         self.x32 = [self.buf.tensor(o["x32_0"], shape, F32, self.device), self.buf.tensor(o["x32_1"], shape, F32, self.device)]
         self.status = self.buf.tensor(o["status"], (1,), torch.int32, self.device)
-        self.peers = {}            # rank -> base pointer of that rank's allocation as mapped into this process
+        self.peers = {plan.rank: self.buf.ptr}   # rank -> base pointer of that rank's allocation as mapped into this process
         self._opened = []
-        self.epoch = 0             # pushes completed so far; identical on every rank
+        self.epoch = 0             # halo pushes completed so far; identical on every rank
+        self.sum_epoch = 0         # sum exchanges started so far; identical on every rank
         self.timeout_s = 30.0
 
     def _offsets(self, Hl):
         n = self.elems(Hl)
         o, cur = {}, 0
         for name, size in (("x64_0", 8 * n), ("x64_1", 8 * n), ("x32_0", 4 * n), ("x32_1", 4 * n),
-                           ("flags", 8 * self.N_FLAGS), ("ticket", 8), ("status", 8)):
+                           ("flags", 8 * self.N_FLAGS), ("mailbox", _ffi.MAILBOX_BYTES), ("ticket", 8), ("status", 8)):
             o[name] = cur
             cur = _align(cur + size)
         o["end"] = cur
@@ -185,13 +207,14 @@ class PeerHaloExchange:
 
     # ---- wiring -------------------------------------------------------------------------------------------
     def connect_ipc(self, group=None):
-        """Exchange IPC handles over ``torch.distributed`` and map the two neighbours' allocations."""
+        """Exchange IPC handles over ``torch.distributed`` and map EVERY other rank's allocation (the halo push needs
+        the two neighbours, the sum exchange all ranks)."""
         import torch.distributed as dist
 
         handles = [None] * self.plan.world
         dist.all_gather_object(handles, self.buf.handle(), group=group)
-        for nb in (self.plan.up, self.plan.down):
-            if nb is not None:
+        for nb in range(self.plan.world):
+            if nb != self.plan.rank:
                 p = C.c_void_p()
                 _ffi.check(_ffi.lib().dpde_peer_open(handles[nb], C.byref(p)))
                 self.peers[nb] = p.value
@@ -199,26 +222,54 @@ class PeerHaloExchange:
         dist.barrier(group=group)
 
     def connect_local(self, others: dict):
-        """All ranks live in this process (``LockstepRanks``): a neighbour's base pointer is just its pointer."""
-        for nb in (self.plan.up, self.plan.down):
-            if nb is not None:
-                self.peers[nb] = others[nb].buf.ptr
+        """All ranks live in this process (``LockstepRanks``): a rank's base pointer is just its pointer."""
+        for nb, other in others.items():
+            self.peers[nb] = other.buf.ptr
+
+    @property
+    def connected(self) -> bool:
+        return len(self.peers) == self.plan.world
 
     def close(self):
-        """Unmap the neighbours' allocations (collective protocol: every rank closes, barrier, then :meth:`free`)."""
+        """Unmap the other ranks' allocations (collective protocol: every rank closes, barrier, then :meth:`free`)."""
         for p in self._opened:
             _ffi.check(_ffi.lib().dpde_peer_close(p))
         self._opened = []
-        self.peers = {}
+        self.peers = {self.plan.rank: self.buf.ptr}
 
     def free(self):
-        """Release this rank's exportable allocation.  Only after every neighbour has closed its mapping."""
+        """Release this rank's exportable allocation.  Only after every other rank has closed its mapping."""
         self.x64, self.x32, self.status = [], [], None
         self.buf.free()
 
-    # ---- per step -----------------------------------------------------------------------------------------
+    # ---- per-step descriptors -----------------------------------------------------------------------------
+    def mailbox(self) -> "_ffi.Mailbox":
+        """``dpde_mailbox`` of the CURRENT sum exchange (``sum_epoch``)."""
+        mb = _ffi.Mailbox()
+        mb.world, mb.rank, mb.epoch = self.plan.world, self.plan.rank, self.sum_epoch
+        for r in range(self.plan.world):
+            mb.boxes[r] = self.peers[r] + self._offsets(self.plan.local_rows(r))["mailbox"]
+        return mb
+
+    def halo_peers(self, parity: int) -> "_ffi.HaloPeers":
+        """``dpde_halo_peers`` for a fused update + push that writes state buffer ``parity``; starts a new push epoch."""
+        p = self.plan
+        self.epoch += 1
+        hp = _ffi.HaloPeers()
+        hp.ticket, hp.epoch = self.buf.ptr + self.offsets["ticket"], self.epoch
+        if p.up is not None:     # I am the LOWER neighbour of my upper neighbour: its "written by the lower neighbour" flag
+            base, off = self.peers[p.up], self._offsets(p.local_rows(p.up))
+            hp.up64, hp.up32, hp.H_up = base + off[f"x64_{parity}"], base + off[f"x32_{parity}"], p.local_rows(p.up)
+            hp.flag_up = base + off["flags"] + 8 * 1
+        if p.down is not None:
+            base, off = self.peers[p.down], self._offsets(p.local_rows(p.down))
+            hp.down64, hp.down32, hp.H_down = base + off[f"x64_{parity}"], base + off[f"x32_{parity}"], p.local_rows(p.down)
+            hp.flag_down = base + off["flags"] + 8 * 0
+        return hp
+
     def push(self, parity: int):
-        """Send the owned boundary rows of state buffer ``parity`` (fp64 and fp32) to both neighbours."""
+        """Stand-alone halo push (one launch per field) of the owned boundary rows of state buffer ``parity``: the
+        unfused path for slabs shorter than 4 halo rows, and the subject of the single-kernel tests."""
         p, h = self.plan, self.plan.halo
         self.epoch += 1
         me = self.offsets
@@ -236,12 +287,13 @@ class PeerHaloExchange:
             _ffi.call("dpde_halo_push", t.data_ptr(), dtype, self.planes, p.H_local, self.W, h,
                       args["up"][0], args["up"][1], args["down"][0], args["down"][1], args["up"][2], args["down"][2],
                       self.epoch, self.buf.ptr + me["ticket"], _stream())
+        self._fields_pushed = 2
 
     def wait(self):
         """Block the stream until the neighbours' pushes of the current epoch have landed in my ghost rows."""
         p = self.plan
         flags = []
-        for k in range(2):
+        for k in range(getattr(self, "_fields_pushed", 1)):
             if p.up is not None:
                 flags.append(self.buf.ptr + self.offsets["flags"] + 8 * (2 * k + 0))
             if p.down is not None:
@@ -256,8 +308,8 @@ class PeerHaloExchange:
         later run on this exchange object starts clean."""
         if int(self.status.item()) != 0:
             self.status.zero_()
-            raise _ffi.DpdeError("dpde_flag_wait timed out: a neighbouring rank never pushed its halo rows; the run's "
-                                 "ghost rows were stale from that step on and its result must be discarded")
+            raise _ffi.DpdeError("a peer-memory wait timed out (dpde_flag_wait / dpde_mailbox_wait_finalize): another rank never "
+                                 "pushed its halo rows or posted its sums; the run's result must be discarded")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -285,6 +337,8 @@ class SlabJointSampler(JointSampler):
         self.peer = None
 
     def _allreduce(self):
+        if self.transport_kind == "peer" and self.plan.world > 1:
+            return self._no_allreduce       # never called: _pass1 / _combine take the mailbox path (only marks "not finalised")
         if self._allreduce_fn is not None:
             return self._allreduce_fn
         if self.plan.world == 1:
@@ -292,6 +346,10 @@ class SlabJointSampler(JointSampler):
         import torch.distributed as dist
         group = self.group
         return lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    @staticmethod
+    def _no_allreduce(sums):
+        raise RuntimeError("SlabJointSampler: the peer transport exchanges its sums through the mailboxes; connect the ranks first")
 
     def begin(self, labels, obs_a, obs_u, mask_a, mask_u, zeta_a, zeta_u, zeta_pde, num_steps=None, sigma_min=None,
               sigma_max=None, rho=None, latents=None, generator=None, connect=True):
@@ -321,10 +379,7 @@ class SlabJointSampler(JointSampler):
         has_u = bool(mask_u.sum() > 0) if C_ - ch_a > 0 else False
 
         def local(t, ch):
-            t = t.to(dev)
-            if t.dtype == torch.bool:
-                t = t.to(torch.uint8)
-            return plan.take(t).contiguous()
+            return plan.take(t.to(dev)).contiguous()      # bool masks stay bool: they reach the kernels as 0 / 1 bytes
 
         coef, dx, llg = None, 0.0, None
         if kind == PDE_HEAT:
@@ -361,12 +416,36 @@ class SlabJointSampler(JointSampler):
                          trace=torch.zeros((num_steps, 4), dtype=F32, device=dev), i=0, allreduce=self._allreduce())
         return self._run
 
+    @property
+    def _peer_exchange(self) -> bool:
+        """The peer-memory product path: mailbox sum exchange + halo push through mapped pointers."""
+        return self.transport_kind == "peer" and self.plan.world > 1 and self.peer is not None and self.peer.connected
+
+    # ---- the three sums: reduce kernel posts into every rank's mailbox; one tiny kernel waits, adds, finalises -----
+    def _pass1(self, r, engine, xN, dx_c, w, i):
+        if not self._peer_exchange:
+            return super()._pass1(r, engine, xN, dx_c, w, i)
+        self.peer.sum_epoch += 1
+        engine.reduce_post(xN, dx_c, w, self.peer.mailbox())
+
+    def _combine(self, r, engine, i):
+        if not self._peer_exchange:
+            return super()._combine(r, engine, i)
+        engine.wait_finalize(self.peer.mailbox(), self.peer.timeout_s, self.peer.status, r["trace"][i])
+
     # owned rows only: ghost rows belong to the neighbours' pushes
     def _launch_update(self, x64, x0_1c, x0_2, g_eu, g_cur, s_cur, s_next, x64n, x32n):
         p, W = self.plan, self.sample_shape[1]
         B, C_ = x64n.shape[0], x64n.shape[1]
-        _ffi.call("dpde_heun_guided_update_rows", x64.data_ptr(), x0_1c.data_ptr(), x0_2.data_ptr() if x0_2 is not None else None,
-                  g_eu.data_ptr() if g_eu is not None else None, g_cur.data_ptr() if g_cur is not None else None,
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        self._fused_push = self._peer_exchange and p.H_local >= 4 * p.halo
+        if self._fused_push:     # update + halo push in one kernel; the next state is buffer parity ^ 1
+            hp = self.peer.halo_peers(self._run["parity"] ^ 1)
+            self.peer._fields_pushed = 1
+            _ffi.call("dpde_heun_guided_update_rows_push", x64.data_ptr(), x0_1c.data_ptr(), ptr(x0_2), ptr(g_eu), ptr(g_cur), s_cur, s_next,
+                      x64n.data_ptr(), x32n.data_ptr(), B * C_, p.H_local, W, p.halo, C.byref(hp), _stream())
+            return
+        _ffi.call("dpde_heun_guided_update_rows", x64.data_ptr(), x0_1c.data_ptr(), ptr(x0_2), ptr(g_eu), ptr(g_cur),
                   s_cur, s_next, x64n.data_ptr(), x32n.data_ptr(), B * C_, p.H_local * W, p.halo * W,
                   (p.H_local - 2 * p.halo) * W, _stream())
 
@@ -376,12 +455,14 @@ class SlabJointSampler(JointSampler):
         self.exchange_push()
 
     def exchange_push(self):
-        """Send the freshly written owned boundary rows of the current state to the neighbours."""
+        """Send the freshly written owned boundary rows of the current state to the neighbours (already done by the
+        fused update + push kernel on the peer path)."""
         r = self._run
         if self.plan.world == 1:
             return
         if self.transport_kind == "peer":
-            self.peer.push(r["parity"])
+            if not getattr(self, "_fused_push", False):
+                self.peer.push(r["parity"])
         elif self.transport_kind == "dist":
             self._dist.exchange(r["x64"], r["x32"])
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DPDE_ABI_VERSION 1
+#define DPDE_ABI_VERSION 2
 
 enum dpde_error { DPDE_OK = 0, DPDE_ERR_INVALID = -1, DPDE_ERR_CUDA = -2, DPDE_ERR_UNSUPPORTED = -3 };
 enum dpde_dtype { DPDE_F32 = 0, DPDE_F64 = 1, DPDE_U8 = 2 };
@@ -64,7 +64,8 @@ typedef struct dpde_guidance_desc {
     int32_t _pad;
     dpde_view x0;              /* denoised estimate x_N (B,C,H,W), F32 or F64                             */
     dpde_view dxdt;            /* its time derivative, same dtype; ptr NULL = zeros (X_and_dXdt_dummy)    */
-    dpde_view obs_a, mask_a;   /* (.., ch_a, H, W) broadcastable; obs F32/F64, mask U8/F32/F64            */
+    dpde_view obs_a, mask_a;   /* (.., ch_a, H, W) broadcastable; obs F32/F64; mask F32/F64 (a weight, multiplied
+                                  as the reference does) or U8 = a boolean mask whose bytes are 0 or 1       */
     dpde_view obs_u, mask_u;   /* (.., C-ch_a, H, W)                                                      */
     const double* sample_coef; /* HEAT: alpha_b = labels[b,-1] (B,);  LLG_RESIDUAL: h_ext in A/m (B,3)    */
     double dx;                 /* grid spacing (square cells, sample.py:133)                              */
@@ -92,7 +93,8 @@ int dpde_set_fast_path(int enable);
 /* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 (default) =
    per pass: 120 columns + 1 halo lane in the reduce pass, 112 + 2 sector aligned in the VJP; 1 / 2 force one of them), key 2 rows per chunk (0 = automatic: up to 128 in the
    VJP, 64 in the reduce pass), keys 3 / 4 = 1 pair every a-plane with the u-plane of the same index in the reduce /
-   VJP pass instead of streaming it as separate work items.  TEST / TUNING HOOK like dpde_set_fast_path: process-wide
+   VJP pass instead of streaming it as separate work items, key 5 = 1 sends interior work items through the general
+   loops instead of the lean interior loops (A/B measurements).  TEST / TUNING HOOK like dpde_set_fast_path: process-wide
    atomics; the per-stream thread-safety of the compute entry points does not extend to changing these concurrently. */
 int dpde_set_tuning(int key, int value);
 
@@ -111,6 +113,33 @@ int dpde_guidance_reduce(const dpde_guidance_desc* desc, void* workspace, double
    can all-reduce `sums` first (batch-coupled semantics / row slabs). */
 int dpde_guidance_finalize(const dpde_guidance_desc* desc, const double* sums, double* scalars, float* trace_row,
                            dpde_stream_t stream);
+
+/* ---- Cross-rank exchange of the three partial sums through peer-memory mailboxes (row slabs, coupled batch shards; new:
+   the reference is single-process).  Every rank owns a zero-initialised DPDE_MAILBOX_BYTES mailbox in memory from
+   dpde_peer_alloc and maps the other ranks' mailboxes (dpde_peer_export / dpde_peer_open); boxes[r] is rank r's mailbox
+   as seen from THIS process (boxes[rank] is the local one).  `epoch` is the step number, >= 1, the same on every rank
+   and increasing by one per exchange: slot [epoch & 1][source rank] is reused two exchanges later, which the protocol
+   itself makes safe (a rank reaches exchange e + 2 only after every rank has finished reading exchange e). */
+#define DPDE_MAX_RANKS 8
+#define DPDE_MAILBOX_BYTES 512
+typedef struct dpde_mailbox {
+    int32_t world, rank;
+    uint64_t epoch;
+    void* boxes[DPDE_MAX_RANKS];
+} dpde_mailbox;
+
+/* dpde_guidance_reduce fused with the first half of the exchange: the last CTA of the reduce pass stores this rank's
+   three sums into slot [epoch & 1][rank] of EVERY rank's mailbox (plain stores through the mapped peer pointers over
+   NVLink) and publishes them with a system-scope release store on the slot's flag.  `sums` receives this rank's
+   partial sums as dpde_guidance_reduce would write them; nothing is finalised. */
+int dpde_guidance_reduce_post(const dpde_guidance_desc* desc, void* workspace, double* sums, const dpde_mailbox* mbox,
+                              dpde_stream_t stream);
+
+/* Second half: blocks the stream until all `world` slots of the local mailbox carry `epoch` (acquire, system scope; after
+   timeout_s seconds it gives up and writes 1 to *status), adds them in rank order -- every rank forms the same total --
+   into sums[3] and runs dpde_guidance_finalize's arithmetic on it. */
+int dpde_mailbox_wait_finalize(const dpde_guidance_desc* desc, const dpde_mailbox* mbox, double timeout_s, int32_t* status,
+                               double* sums, double* scalars, float* trace_row, dpde_stream_t stream);
 
 /* Pass 2 -- analytic vector-Jacobian product replacing autograd through sample.py:336-353:
    g_x0 (B,C,H,W contiguous, dtype of x0) = d loss_comb / d x_N;  g_dxdt (same shape, may be NULL) = d / d dxdt.
@@ -166,6 +195,31 @@ int dpde_heun_guided_update_rows(const double* x_cur, const float* x0_cur, const
                                  const float* g_cur, double sigma_cur, double sigma_next, double* x_next64,
                                  float* x_next32, int64_t planes, int64_t plane_elems, int64_t first, int64_t count,
                                  dpde_stream_t stream);
+
+/* The same update fused with the halo exchange of a row slab (one kernel: compute + transfer over NVLink peer memory).
+   The fields are planes x H_local x W local buffers with `halo` ghost rows per side; the owned rows [halo, H_local - halo)
+   are updated.  The 2 x halo owned BOUNDARY rows are processed first and every element of them is stored twice: into this
+   rank's next-state buffers and straight into the neighbours' ghost rows (up64 / up32: the upper neighbour's next-state
+   buffers, H_up rows per plane, written at rows [H_up - halo, H_up); down64 / down32 at rows [0, halo)).  When the last CTA
+   that holds boundary rows has fenced its peer stores (system scope), `epoch` is stored with release semantics into
+   *flag_up / *flag_down (8-byte words in the neighbours' memory) -- while the remaining CTAs are still updating interior
+   rows, so the transfer overlaps the bulk of the update.  NULL pointers on a side = grid boundary.  `ticket`: zeroed 4-byte
+   word in local device memory (left zeroed).  Needs H_local >= 4 halo (boundary rows of the two sides disjoint). */
+typedef struct dpde_halo_peers {
+    double* up64;
+    float* up32;
+    double* down64;
+    float* down32;
+    void* flag_up;
+    void* flag_down;
+    void* ticket;
+    uint64_t epoch;
+    int32_t H_up, H_down;
+} dpde_halo_peers;
+int dpde_heun_guided_update_rows_push(const double* x_cur, const float* x0_cur, const float* x0_next, const float* g_eu,
+                                      const float* g_cur, double sigma_cur, double sigma_next, double* x_next64,
+                                      float* x_next32, int64_t planes, int32_t H_local, int32_t W, int32_t halo,
+                                      const dpde_halo_peers* peers, dpde_stream_t stream);
 
 /* ---- Peer memory: row-slab halo exchange over NVLink (one process per GPU; nothing like it in the reference) ----
    dpde_peer_alloc returns zero-filled device memory that can be exported to the other ranks of the box

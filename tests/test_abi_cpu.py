@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(ffi):
     L = ffi.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.dpde_abi_version() == 1
+    assert L.dpde_abi_version() == ffi.ABI_VERSION == 2
     assert L.dpde_guidance_workspace_bytes() >= 3 * 8 * 148
 
 
@@ -38,13 +38,19 @@ def test_struct_layout_matches_the_c_compiler(ffi, tmp_path):
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dpde_b200.h"\nint main(void){'
                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dpde_view), sizeof(dpde_guidance_desc),'
                    'offsetof(dpde_guidance_desc, x0), offsetof(dpde_guidance_desc, mask_u), offsetof(dpde_guidance_desc, sample_coef),'
-                   'offsetof(dpde_guidance_desc, dx), offsetof(dpde_guidance_desc, gamma), offsetof(dpde_guidance_desc, easy_axis));return 0;}\n')
+                   'offsetof(dpde_guidance_desc, dx), offsetof(dpde_guidance_desc, gamma), offsetof(dpde_guidance_desc, easy_axis));'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(dpde_mailbox), offsetof(dpde_mailbox, epoch), offsetof(dpde_mailbox, boxes),'
+                   'sizeof(dpde_halo_peers), offsetof(dpde_halo_peers, ticket), offsetof(dpde_halo_peers, epoch), offsetof(dpde_halo_peers, H_down),'
+                   'DPDE_MAX_RANKS, DPDE_MAILBOX_BYTES);return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     D = ffi.GuidanceDesc
+    M, P = ffi.Mailbox, ffi.HaloPeers
     want = [C.sizeof(ffi.View), C.sizeof(D), D.x0.offset, D.mask_u.offset, D.sample_coef.offset, D.dx.offset, D.gamma.offset,
-            D.easy_axis.offset]
+            D.easy_axis.offset,
+            C.sizeof(M), M.epoch.offset, M.boxes.offset, C.sizeof(P), P.ticket.offset, P.epoch.offset, P.H_down.offset,
+            ffi.MAX_RANKS, ffi.MAILBOX_BYTES]
     assert got == want
 
 
@@ -66,6 +72,20 @@ def test_argument_validation_without_a_gpu(ffi):
     assert b"3 magnetisation" in L.dpde_last_error()
     with pytest.raises(ffi.DpdeError):
         ffi.call("dpde_halo_pack", None, 0, 1, 8, 8, 2, None, None, None)
+    # mailbox exchange and the fused update + push: bad descriptors never reach a launch
+    d.pde_kind, d.C, d.sample_coef, d.dx = ffi.PDE_HEAT, 2, 1, 0.1
+    mb = ffi.Mailbox()
+    mb.world, mb.rank, mb.epoch = 9, 0, 1
+    assert L.dpde_guidance_reduce_post(C.byref(d), 1, 1, C.byref(mb), None) == -1 and b"world" in L.dpde_last_error()
+    mb.world, mb.epoch = 2, 0
+    assert L.dpde_mailbox_wait_finalize(C.byref(d), C.byref(mb), 1.0, None, 1, 1, None, None) == -1 and b"epoch" in L.dpde_last_error()
+    mb.epoch = 1
+    assert L.dpde_mailbox_wait_finalize(C.byref(d), C.byref(mb), 1.0, None, 1, 1, None, None) == -1 and b"boxes[0]" in L.dpde_last_error()
+    hp = ffi.HaloPeers()
+    assert L.dpde_heun_guided_update_rows_push(1, 1, None, None, None, 1.0, 0.0, 1, 1, 2, 7, 8, 2, C.byref(hp), None) == -1
+    assert b"4 halo" in L.dpde_last_error()
+    assert L.dpde_heun_guided_update_rows_push(1, 1, None, None, None, 1.0, 0.0, 1, 1, 2, 8, 8, 2, C.byref(hp), None) == -1
+    assert b"ticket" in L.dpde_last_error()
 
 
 def test_product_has_no_cpu_path():

@@ -203,6 +203,48 @@ def test_tuning_knobs_never_change_results(tune):
     assert _ffi.lib().dpde_set_tuning(99, 0) != 0
 
 
+@pytest.mark.parametrize("shape", [(2, 1, 1, 100, 520), (1, 1, 2, 76, 400), (2, 0, 1, 64, 1024)])
+@pytest.mark.parametrize("rows", [8, 16, 14, 30])
+@pytest.mark.parametrize("obs", [True, False])
+def test_heat_interior_loops_match_closed_form(shape, rows, obs):
+    """The lean interior loops of the marching kernels (full chunks away from the grid boundary, strips without an
+    edge column): chunk lengths that make the reduce pass (8, 16) resp. the VJP (14, 30: R + 2 a multiple of its ring
+    depth) take them on these small grids, against the closed form and against the general loops (tuning key 5)."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_HEAT
+
+    B, ch_a, cu, H, W = shape
+    x0, dxdt, labels, obs_a, obs_u, mask_a, mask_u = _heat_case(B, max(ch_a, 1), cu, H, W, seed=H + W + rows)
+    if ch_a == 0:
+        x0, dxdt = x0[:, 1:].contiguous(), dxdt[:, 1:].contiguous()
+    if not obs:
+        mask_u = torch.zeros_like(mask_u)
+    dx, w, dev = 1.0 / (H - 1), (20.0, 0.5, 20.0), _dev()
+
+    def run():
+        eng = GuidanceEngine(B, ch_a + cu, ch_a, H, W, PDE_HEAT, dev, obs_a=obs_a.to(dev) if ch_a else None,
+                             mask_a=mask_a.to(dev) if ch_a else None, obs_u=obs_u.to(dev), mask_u=mask_u.to(dev),
+                             sample_coef=labels[:, -1].double().to(dev), dx=dx)
+        g, _ = eng.seed(x0.to(dev), dxdt.to(dev), w)
+        return eng.scalars[:4].clone(), g
+
+    try:
+        _ffi.check(_ffi.lib().dpde_set_tuning(2, rows))
+        s_lean, g_lean = run()
+        _ffi.check(_ffi.lib().dpde_set_tuning(5, 1))
+        s_gen, g_gen = run()
+    finally:
+        _ffi.check(_ffi.lib().dpde_set_tuning(2, 0))
+        _ffi.check(_ffi.lib().dpde_set_tuning(5, 0))
+    oa, ma = (np.asarray(obs_a, np.float64), np.asarray(mask_a, np.float64)) if ch_a else (np.zeros((B, 0, H, W)), np.zeros((H, W)))
+    losses, g_ref, _ = R.heat_guidance_numpy(x0.double().numpy(), dxdt.double().numpy(), labels[:, -1].double().numpy(), dx, oa,
+                                             obs_u.double().numpy(), ma, mask_u.double().numpy(), ch_a, *w)
+    _close(s_lean, np.array(losses), 1e-12, "losses (lean loops)")
+    _close(g_lean, g_ref, RTOL32, "seed gradient (lean loops)")
+    _close(s_gen, s_lean, 1e-13, "losses, general vs lean loops")
+    _close(g_gen, g_lean, 2e-7, "seed gradient, general vs lean loops")
+
+
 def test_heat_guidance_fp64_fields_and_autograd_cross_check():
     """fp64 fields (what the unmodified sampler holds) and an independent check against torch autograd on the device."""
     from dynamical_pde_diffusion_b200 import GuidanceEngine

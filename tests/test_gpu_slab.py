@@ -93,6 +93,119 @@ def test_halo_push_and_flag_wait_single_process(dtype, W):
         b.free()
 
 
+@pytest.mark.parametrize("W", [16, 10])
+@pytest.mark.parametrize("last", [False, True])
+def test_fused_update_and_halo_push_single_process(W, last):
+    """dpde_heun_guided_update_rows_push: three 'ranks' as three buffers of one device.  Owned rows equal the flat update,
+    ghost rows are untouched locally, the neighbours' ghost rows receive the freshly updated boundary rows (fp64 and
+    fp32), the flags carry the epoch.  Pushes first, waits afterwards."""
+    from dynamical_pde_diffusion_b200 import _ffi
+    from dynamical_pde_diffusion_b200.slab import PeerBuffer
+
+    dev, planes, halo = _dev(), 3, 2
+    Hs = [9, 8, 12]
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(3)
+    ctl = PeerBuffer(1024)
+    flags = ctl.tensor(0, (6,), torch.int64, dev)
+    status = ctl.tensor(512, (1,), torch.int32, dev)
+    fl = lambda rank, side: ctl.ptr + 8 * (2 * rank + side)
+    ins, outs, want = [], [], []
+    for h in Hs:
+        x = torch.randn(planes, h, W, generator=g, dtype=torch.float64).to(dev)
+        a, b, ge, gc = (torch.randn(planes, h, W, generator=g).to(dev) for _ in range(4))
+        o64, o32 = torch.full_like(x, 7.0), torch.full_like(a, 7.0)
+        f64, f32 = torch.empty_like(x), torch.empty_like(a)
+        _ffi.call("dpde_heun_guided_update", x.data_ptr(), a.data_ptr(), None if last else b.data_ptr(), None if last else ge.data_ptr(),
+                  gc.data_ptr(), 3.0, 0.0 if last else 2.0, f64.data_ptr(), f32.data_ptr(), x.numel(), s)
+        ins.append((x, a, b, ge, gc))
+        outs.append((o64, o32))
+        want.append((f64, f32))
+    for r in range(3):
+        up, down = (r - 1 if r > 0 else None), (r + 1 if r < 2 else None)
+        hp = _ffi.HaloPeers()
+        hp.ticket, hp.epoch = ctl.ptr + 256, 4
+        if up is not None:
+            hp.up64, hp.up32, hp.H_up, hp.flag_up = outs[up][0].data_ptr(), outs[up][1].data_ptr(), Hs[up], fl(up, 1)
+        if down is not None:
+            hp.down64, hp.down32, hp.H_down, hp.flag_down = outs[down][0].data_ptr(), outs[down][1].data_ptr(), Hs[down], fl(down, 0)
+        x, a, b, ge, gc = ins[r]
+        _ffi.call("dpde_heun_guided_update_rows_push", x.data_ptr(), a.data_ptr(), None if last else b.data_ptr(),
+                  None if last else ge.data_ptr(), gc.data_ptr(), 3.0, 0.0 if last else 2.0, outs[r][0].data_ptr(), outs[r][1].data_ptr(),
+                  planes, Hs[r], W, halo, C.byref(hp), s)
+    for r in range(3):
+        mine = [fl(r, side) for side, nb in ((0, r - 1), (1, r + 1)) if 0 <= nb < 3]
+        arr = (C.c_void_p * len(mine))(*mine)
+        _ffi.call("dpde_flag_wait", arr, len(mine), 4, 5.0, status.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0 and flags.tolist() == [0, 4, 4, 4, 4, 0]
+    for r in range(3):
+        for k in range(2):
+            got, ref = outs[r][k], want[r][k]
+            assert torch.equal(got[:, halo:Hs[r] - halo], ref[:, halo:Hs[r] - halo]), (r, k)
+            top = want[r - 1][k][:, Hs[r - 1] - 2 * halo:Hs[r - 1] - halo] if r > 0 else torch.full_like(ref[:, :halo], 7.0)
+            bot = want[r + 1][k][:, halo:2 * halo] if r < 2 else torch.full_like(ref[:, :halo], 7.0)
+            assert torch.equal(got[:, :halo], top) and torch.equal(got[:, Hs[r] - halo:], bot), (r, k)
+    del flags, status
+    ctl.free()
+
+
+def test_mailbox_sum_exchange_single_process():
+    """dpde_guidance_reduce_post + dpde_mailbox_wait_finalize with three 'ranks' (row slabs of one grid) on one device: posts
+    first, waits afterwards.  Every rank finalises the same totals, equal to the whole-grid reduce up to summation order;
+    two consecutive epochs exercise both slot parities; a missing post times out and is reported."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_HEAT
+    from dynamical_pde_diffusion_b200.slab import PeerBuffer, SlabPlan
+
+    dev, B, H, W, world = _dev(), 2, 36, 20, 3
+    g = torch.Generator().manual_seed(5)
+    x0, dxdt = torch.randn(B, 2, H, W, generator=g), 0.3 * torch.randn(B, 2, H, W, generator=g)
+    obs_a, obs_u = torch.randn(1, 1, H, W, generator=g), torch.randn(1, 1, H, W, generator=g)
+    mask_a, mask_u = torch.rand(H, W, generator=g) < 0.3, torch.rand(H, W, generator=g) < 0.2
+    coef, dx, w = torch.rand(B, generator=g).double(), 1.0 / (H - 1), (20.0, 0.5, 20.0)
+    whole = GuidanceEngine(B, 2, 1, H, W, PDE_HEAT, dev, obs_a=obs_a.to(dev), mask_a=mask_a.to(dev), obs_u=obs_u.to(dev), mask_u=mask_u.to(dev),
+                           sample_coef=coef.to(dev), dx=dx)
+    whole.reduce(x0.to(dev), dxdt.to(dev), w)
+    boxes = [PeerBuffer(_ffi.MAILBOX_BYTES) for _ in range(world)]
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    plans = [SlabPlan(H, world, r) for r in range(world)]
+    engs = [GuidanceEngine(B, 2, 1, p.H_local, W, PDE_HEAT, dev, obs_a=p.take(obs_a).to(dev), mask_a=p.take(mask_a).to(dev),
+                           obs_u=p.take(obs_u).to(dev), mask_u=p.take(mask_u).to(dev), sample_coef=coef.to(dev), dx=dx,
+                           slab=dict(halo=p.halo, row0=p.r0, H_global=H, has_a=True, has_u=True)) for p in plans]
+
+    def mbox(rank, epoch):
+        mb = _ffi.Mailbox()
+        mb.world, mb.rank, mb.epoch = world, rank, epoch
+        for r in range(world):
+            mb.boxes[r] = boxes[r].ptr
+        return mb
+
+    for epoch in (1, 2):
+        scale = float(epoch)                                          # different data per epoch
+        for r, (p, e) in enumerate(zip(plans, engs)):
+            e.reduce_post(p.take(scale * x0).contiguous().to(dev), p.take(dxdt).contiguous().to(dev), w, mbox(r, epoch))
+        traces = torch.zeros(world, 4, device=dev)
+        for r, e in enumerate(engs):
+            e.wait_finalize(mbox(r, epoch), 5.0, status, traces[r])
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        whole.reduce(scale * x0.to(dev), dxdt.to(dev), w)
+        for r, e in enumerate(engs):
+            assert torch.equal(e.sums, engs[0].sums) and torch.equal(e.scalars, engs[0].scalars)      # same order on every rank
+            torch.testing.assert_close(e.sums, whole.sums, rtol=1e-13, atol=0)
+            torch.testing.assert_close(e.scalars[:7], whole.scalars[:7], rtol=1e-13, atol=0)
+            torch.testing.assert_close(traces[r], whole.scalars[:4].float(), rtol=1e-6, atol=0)
+    # epoch 3: rank 2 never posts -> the others report a timeout instead of hanging
+    for r in (0, 1):
+        engs[r].reduce_post(plans[r].take(x0).contiguous().to(dev), plans[r].take(dxdt).contiguous().to(dev), w, mbox(r, 3))
+    engs[0].wait_finalize(mbox(0, 3), 0.05, status, None)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 1
+    for b in boxes:
+        b.free()
+
+
 def _heat_inputs(B, H, W, seed=0):
     g = torch.Generator().manual_seed(seed)
     labels = torch.stack([0.5 * torch.rand(B, generator=g), torch.exp(-2.5 + 3 * torch.rand(B, generator=g))], 1).float()
