@@ -46,7 +46,8 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Sum three per-thread doubles over the CTA; result valid in thread 0.  `scratch` holds 3 * (kThreads/32) doubles.
+// Sum three per-thread doubles over a CTA of NT threads; result valid in thread 0.  `scratch` holds 3 * (NT/32) doubles.
+template <int NT = kThreads>
 __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* scratch) {
     a = warp_sum(a);
     b = warp_sum(b);
@@ -59,7 +60,7 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
     }
     __syncthreads();
     if (warp == 0) {
-        constexpr int nw = kThreads / 32;
+        constexpr int nw = NT / 32;
         a = lane < nw ? scratch[lane * 3 + 0] : 0.0;
         b = lane < nw ? scratch[lane * 3 + 1] : 0.0;
         c = lane < nw ? scratch[lane * 3 + 2] : 0.0;

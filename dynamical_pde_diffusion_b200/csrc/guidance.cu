@@ -196,16 +196,18 @@ __device__ __forceinline__ void finalize_scalars(const Params& p, const double* 
 //      rank's mailbox over NVLink peer memory: thread r stores the three doubles into slot [epoch & 1][my rank] of rank
 //      r's mailbox and publishes them with st.release.sys on the slot's flag word.  dpde_mailbox_wait_finalize on each
 //      rank acquires the `world` flags and adds the slots in rank order, so every rank forms the same total.
-__device__ __forceinline__ void reduce_epilogue(const Params& p, double s_a, double s_u, double s_p, double* scratch, bool* is_last,
-                                                double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                                double* __restrict__ sums, int finalize, double* __restrict__ scal,
-                                                float* __restrict__ trace) {
+template <int NT>
+__device__ __forceinline__ void reduce_epilogue_n(const Params& p, double s_a, double s_u, double s_p, double* scratch, bool* is_last,
+                                                  double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                  double* __restrict__ sums, int finalize, double* __restrict__ scal,
+                                                  float* __restrict__ trace, int part_base = 0) {
+    // part_base > 0: an earlier kernel of the same stream (the LEAN kernel of a pass) already filled slots [0, part_base)
     const int tid = threadIdx.x;
-    block_sum3(s_a, s_u, s_p, scratch);
+    block_sum3<NT>(s_a, s_u, s_p, scratch);
     if (tid == 0) {
-        partials[3 * blockIdx.x + 0] = s_a;
-        partials[3 * blockIdx.x + 1] = s_u;
-        partials[3 * blockIdx.x + 2] = s_p;
+        partials[3 * (part_base + blockIdx.x) + 0] = s_a;
+        partials[3 * (part_base + blockIdx.x) + 1] = s_u;
+        partials[3 * (part_base + blockIdx.x) + 2] = s_p;
         __threadfence();
         *is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
@@ -213,12 +215,12 @@ __device__ __forceinline__ void reduce_epilogue(const Params& p, double s_a, dou
     if (!*is_last) return;
     __threadfence();
     double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
+    for (int i = tid; i < part_base + (int)gridDim.x; i += NT) {
         a += __ldcg(partials + 3 * i);
         b += __ldcg(partials + 3 * i + 1);
         c += __ldcg(partials + 3 * i + 2);
     }
-    block_sum3(a, b, c, scratch);
+    block_sum3<NT>(a, b, c, scratch);
     if (tid == 0) {
         sums[0] = a;
         sums[1] = b;
@@ -239,6 +241,13 @@ __device__ __forceinline__ void reduce_epilogue(const Params& p, double s_a, dou
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&slot->flag), "l"(p.mb_epoch) : "memory");
         }
     }
+}
+
+__device__ __forceinline__ void reduce_epilogue(const Params& p, double s_a, double s_u, double s_p, double* scratch, bool* is_last,
+                                                double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                double* __restrict__ sums, int finalize, double* __restrict__ scal,
+                                                float* __restrict__ trace) {
+    reduce_epilogue_n<kThreads>(p, s_a, s_u, s_p, scratch, is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
 // =========================================================================================================
@@ -731,6 +740,7 @@ heat_residual_sq_vjp_kernel(const T* __restrict__ u, const T* __restrict__ dudt,
 
 #include "heat_march.cuh"
 #include "llg_tile.cuh"
+#include "llg_march.cuh"
 
 // =========================================================================================================
 // host side
@@ -743,7 +753,8 @@ std::atomic<bool> g_fast_path{true};
 // sector aligned), 1 = 120 + 1 in both, 2 = 112 + 2 in both;
 // [1] unused; [2] rows per chunk (0 = automatic); [3] / [4] 1 = pair a-planes with u-planes in the
 // reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s);
-// [5] 1 = interior work items take the general loops too (A/B runs of the lean interior loops)
+// [5] 1 = interior work items take the general loops too (A/B runs of the lean interior loops);
+// [6] 1 = the LLG m x H_eff residual runs the round-1 tile kernels on every width (default: marching kernels for W >= 128)
 std::atomic<int> g_tuning[8] = {};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -772,9 +783,14 @@ bool march_eligible(const Params& p, const void* g_x0, const void* g_dxdt) {
     return true;
 }
 
-MarchGeom march_geometry(const Params& p, bool vjp) {
-    MarchGeom g;
-    g.lean = g_tuning[5] == 0;
+// 0: a-planes are separate streaming items; 1: paired with the u-plane of the same index; 2: paired, mask_a empty
+inline int pairing(const Params& p, bool vjp) {
+    return ((vjp ? g_tuning[4] != 0 : g_tuning[3] != 0) && p.ch_a >= 1 && p.ch_a == p.n_u_units) ? (p.has_a ? 1 : 2) : 0;
+}
+
+// `lean_ok`: may interior work items go to the LEAN kernel (no g_dxdt output in the VJP, a-planes not paired)?
+MarchGeom march_geometry(const Params& p, bool vjp, bool lean_ok = true) {
+    MarchGeom g{};
     const int rows = p.yhi - p.ylo;
     if (p.W <= 128) {
         int lw = 1, l2 = 0;
@@ -808,18 +824,32 @@ MarchGeom march_geometry(const Params& p, bool vjp) {
     g.a_block4 = stream_block4(g.a_plane4, (int64_t)(p.ch_a > 0 ? p.ch_a : 1) * p.B);
     g.a_blocks_per_plane = (g.a_plane4 + g.a_block4 - 1) / g.a_block4;
     g.n_a_items = g.a_blocks_per_plane * p.ch_a * p.B;
+    // ---- interior rectangle (heat_march.cuh, "Three kernels"): strips none of whose 32 lanes is an edge or idle lane,
+    //      full chunks whose rows + stencil margin need neither reflection nor clamping, row iterations in whole groups
+    g.n_int_items = 0;
+    const int n_it = vjp ? R + 2 : R, margin = vjp ? 2 : 1;
+    if (lean_ok && g_tuning[5] == 0 && g.segs_per_warp == 1 && pairing(p, vjp) == 0 && n_it % kLeanRing == 0 && n_it >= (vjp ? 2 : 1) * kLeanRing) {
+        int s_lo = -1, s_hi = -2, c_lo = -1, c_hi = -2;
+        for (int st = 0; st < g.strips; ++st) {
+            const int first = st * g.strip_w - 4 * g.halo_lane, last = first + 4 * 31;
+            if (first >= 4 && last + 4 < p.W) { if (s_lo < 0) s_lo = st; s_hi = st; }
+        }
+        for (int c = 0; c < g.chunks; ++c) {
+            const int ys = p.ylo + c * R;
+            if (ys + R <= p.yhi && rows_inside(p, ys - margin, ys + R + margin - 1)) { if (c_lo < 0) c_lo = c; c_hi = c; }
+        }
+        if (s_lo >= 0 && c_lo >= 0) {
+            g.s_lo = s_lo; g.s_hi = s_hi; g.c_lo = c_lo; g.c_hi = c_hi;
+            g.n_int_items = p.B * p.n_u_units * (s_hi - s_lo + 1) * (c_hi - c_lo + 1);
+        }
+    }
     return g;
 }
 
-// 0: a-planes are separate streaming items; 1: paired with the u-plane of the same index; 2: paired, mask_a empty
-inline int pairing(const Params& p, bool vjp) {
-    return ((vjp ? g_tuning[4] != 0 : g_tuning[3] != 0) && p.ch_a >= 1 && p.ch_a == p.n_u_units) ? (p.has_a ? 1 : 2) : 0;
-}
-
+// Opt a kernel instantiation in to > 48 KB of dynamic shared memory (once per instantiation AND device: the attribute is
+// per device and a process may drive several GPUs) and return its occupancy.
 template <typename K>
-int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
-    // opt in to > 48 KB dynamic shared memory once per kernel instantiation AND device (the attribute is per device;
-    // a process may drive several GPUs), then size a persistent grid
+int march_occupancy(K kernel, int smem) {
     static thread_local const void* configured[16][64] = {{nullptr}};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -833,19 +863,46 @@ int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
     }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-    int64_t need = ((int64_t)g.n_warp_items + (paired ? 0 : g.n_a_items) + kThreads / 32 - 1) / (kThreads / 32);
-    int64_t grid = (int64_t)sm_count() * occ;
+    return occ;
+}
+
+inline int clamp_grid(int64_t grid, int64_t need, int64_t cap) {
     if (grid > need) grid = need;
-    if (grid > kMaxPartials) grid = kMaxPartials;
+    if (grid > cap) grid = cap;
     return (int)(grid < 1 ? 1 : grid);
 }
 
-template <bool HAS_D, bool HAS_O, int PA>
-int launch_march_reduce_pa(const Params& p, const MarchGeom& g, double* partials, unsigned int* ticket, double* sums, int finalize,
-                           double* scal, float* trace, cudaStream_t s) {
+template <typename K>
+int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
+    const int occ = march_occupancy(kernel, smem);
+    const int64_t need = ((int64_t)g.n_warp_items + (paired ? 0 : g.n_a_items) + kThreads / 32 - 1) / (kThreads / 32);
+    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials / 2);
+}
+
+template <typename K>
+int lean_grid(K kernel, const MarchGeom& g) {
+    const int occ = march_occupancy(kernel, lean_ring_bytes());
+    const int64_t need = ((int64_t)g.n_int_items + kThreads / 32 - 1) / (kThreads / 32);
+    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials / 2);
+}
+
+// One pass = the LEAN kernel over the interior rectangle (when there is one) + the REST kernel, or the single ALL kernel.
+template <bool HAS_D, bool HAS_O, int PA, bool PS>
+int launch_march_reduce_parts(const Params& p, MarchGeom g, double* partials, unsigned int* ticket, double* sums, int finalize,
+                              double* scal, float* trace, cudaStream_t s) {
     constexpr int smem = ring_bytes(PA, false);
-    auto k = heat_march_reduce_kernel<HAS_D, HAS_O, PA>;
-    k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    if (PA == 0 && g.n_int_items > 0) {
+        auto lean = heat_march_reduce_kernel<HAS_D, HAS_O, 0, PS, PART_LEAN>;
+        const int grid_a = lean_grid(lean, g);
+        lean<<<grid_a, kThreads, lean_ring_bytes(), s>>>(p, g, partials, ticket, sums, 0, scal, trace);
+        g.part_base = grid_a;
+        auto rest = heat_march_reduce_kernel<HAS_D, HAS_O, 0, PS, PART_REST>;
+        rest<<<march_grid(rest, g, smem, false), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    } else {
+        g.n_int_items = 0;
+        auto k = heat_march_reduce_kernel<HAS_D, HAS_O, PA, PS, PART_ALL>;
+        k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    }
     return check_launch("dpde_guidance_reduce (march)");
 }
 
@@ -854,28 +911,36 @@ int launch_march_reduce(const Params& p, double* partials, unsigned int* ticket,
                         float* trace, cudaStream_t s) {
     const MarchGeom g = march_geometry(p, false);
     switch (pairing(p, false)) {
-        case 1: return launch_march_reduce_pa<HAS_D, HAS_O, 1>(p, g, partials, ticket, sums, finalize, scal, trace, s);
-        case 2: return launch_march_reduce_pa<HAS_D, HAS_O, 2>(p, g, partials, ticket, sums, finalize, scal, trace, s);
-        default: return launch_march_reduce_pa<HAS_D, HAS_O, 0>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        case 1: return launch_march_reduce_parts<HAS_D, HAS_O, 1, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        case 2: return launch_march_reduce_parts<HAS_D, HAS_O, 2, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        default: return launch_march_reduce_parts<HAS_D, HAS_O, 0, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
     }
 }
 
-template <bool HAS_D, bool HAS_O, int PA>
-int launch_march_vjp_pa(const Params& p, const MarchGeom& g, const double* scal, const double* upstream, float* g_x0,
-                        float* g_dxdt, cudaStream_t s) {
+template <bool HAS_D, bool HAS_O, int PA, bool PS>
+int launch_march_vjp_parts(const Params& p, MarchGeom g, const double* scal, const double* upstream, float* g_x0, float* g_dxdt,
+                           cudaStream_t s) {
     constexpr int smem = ring_bytes(PA, true);
-    auto k = heat_march_vjp_kernel<HAS_D, HAS_O, PA>;
-    k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    if (PA == 0 && g.n_int_items > 0) {
+        auto lean = heat_march_vjp_kernel<HAS_D, HAS_O, 0, PS, PART_LEAN>;
+        lean<<<lean_grid(lean, g), kThreads, lean_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+        auto rest = heat_march_vjp_kernel<HAS_D, HAS_O, 0, PS, PART_REST>;
+        rest<<<march_grid(rest, g, smem, false), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    } else {
+        g.n_int_items = 0;
+        auto k = heat_march_vjp_kernel<HAS_D, HAS_O, PA, PS, PART_ALL>;
+        k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    }
     return check_launch("dpde_guidance_vjp (march)");
 }
 
 template <bool HAS_D, bool HAS_O>
 int launch_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
-    const MarchGeom g = march_geometry(p, true);
+    const MarchGeom g = march_geometry(p, true, g_dxdt == nullptr);
     switch (pairing(p, true)) {
-        case 1: return launch_march_vjp_pa<HAS_D, HAS_O, 1>(p, g, scal, upstream, g_x0, g_dxdt, s);
-        case 2: return launch_march_vjp_pa<HAS_D, HAS_O, 2>(p, g, scal, upstream, g_x0, g_dxdt, s);
-        default: return launch_march_vjp_pa<HAS_D, HAS_O, 0>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        case 1: return launch_march_vjp_parts<HAS_D, HAS_O, 1, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        case 2: return launch_march_vjp_parts<HAS_D, HAS_O, 2, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        default: return launch_march_vjp_parts<HAS_D, HAS_O, 0, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
     }
 }
 
@@ -956,8 +1021,93 @@ int launch_llg_tile_vjp(const Params& p, const LlgGeom& L, const double* scal, c
     return check_launch("dpde_guidance_vjp (llg tile)");
 }
 
+// ---- LLG m x H_eff residual, marching kernels (llg_march.cuh) ---------------------------------------------
+inline bool llg_march_wanted(const Params& p) { return p.kind == DPDE_PDE_LLG_RESIDUAL && p.W >= 128 && g_tuning[6] == 0; }
+
+LlgMarchGeom llg_march_geometry(const Params& p, bool vjp, bool lean_ok) {
+    LlgMarchGeom g{};
+    const int rows = p.yhi - p.ylo;
+    g.strips = (p.W + kLlgStrip - 1) / kLlgStrip;
+    const int64_t per_row_items = (int64_t)g.strips * p.B;
+    // rows per chunk: long chunks amortise the warm-up rows, short ones give every resident warp (12 per SM) a few items
+    const int64_t want_warps = (int64_t)sm_count() * 12;
+    int R = 64;
+    while (R > 8 && ((rows + R - 1) / R) * per_row_items < 2 * want_warps) R >>= 1;
+    if (vjp) R -= 2;                         // R + 2 row iterations in groups of the ring depth (4): 62, 30, 14, 6
+    if (g_tuning[2] > 0) R = g_tuning[2];
+    g.R = R;
+    g.chunks = (rows + R - 1) / R;
+    g.n_items = (int)((int64_t)g.chunks * per_row_items);
+    g.a.a_plane4 = (int)((int64_t)rows * p.W / 4);
+    g.a.a_block4 = stream_block4(g.a.a_plane4, p.B);
+    g.a.a_blocks_per_plane = (g.a.a_plane4 + g.a.a_block4 - 1) / g.a.a_block4;
+    g.a.n_a_items = g.a.a_blocks_per_plane * p.ch_a * p.B;
+    // interior rectangle: strips whose 32 lanes all hold grid columns away from the edge columns, full chunks whose rows +
+    // stencil margin need neither reflection nor clamping, row iterations in whole groups of the ring depth
+    const int n_it = vjp ? R + 2 : R, margin = vjp ? 2 : 1;
+    if (lean_ok && g_tuning[5] == 0 && n_it % kLR == 0 && n_it >= (vjp ? 2 : 1) * kLR) {
+        int s_lo = -1, s_hi = -2, c_lo = -1, c_hi = -2;
+        for (int st = 0; st < g.strips; ++st) {
+            const int first = st * kLlgStrip - 2, last = first + 2 * 31;
+            if (first >= 2 && last + 2 < p.W) { if (s_lo < 0) s_lo = st; s_hi = st; }
+        }
+        for (int c = 0; c < g.chunks; ++c) {
+            const int ys = p.ylo + c * R;
+            if (ys + R <= p.yhi && rows_inside(p, ys - margin, ys + R + margin - 1)) { if (c_lo < 0) c_lo = c; c_hi = c; }
+        }
+        if (s_lo >= 0 && c_lo >= 0) {
+            g.s_lo = s_lo; g.s_hi = s_hi; g.c_lo = c_lo; g.c_hi = c_hi;
+            g.n_int_items = p.B * (s_hi - s_lo + 1) * (c_hi - c_lo + 1);
+        }
+    }
+    return g;
+}
+
+template <typename K>
+int llg_march_grid(K kernel, int64_t warp_items) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLlgThreads, llg_ring_bytes()) != cudaSuccess || occ < 1) occ = 1;
+    const int64_t need = (warp_items + kLlgThreads / 32 - 1) / (kLlgThreads / 32);
+    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials / 2);
+}
+
+template <bool HAS_D, bool HAS_O>
+int launch_llg_march_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal, float* trace,
+                            cudaStream_t s) {
+    LlgMarchGeom g = llg_march_geometry(p, false, true);
+    if (g.n_int_items > 0) {
+        auto lean = llg_march_reduce_kernel<HAS_D, HAS_O, PART_LEAN>;
+        const int grid_a = llg_march_grid(lean, g.n_int_items);
+        lean<<<grid_a, kLlgThreads, llg_ring_bytes(), s>>>(p, g, partials, ticket, sums, 0, scal, trace);
+        g.part_base = grid_a;
+    }
+    auto rest = llg_march_reduce_kernel<HAS_D, HAS_O, PART_REST>;
+    rest<<<llg_march_grid(rest, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, partials, ticket, sums, finalize,
+                                                                                                       scal, trace);
+    return check_launch("dpde_guidance_reduce (llg march)");
+}
+
+template <bool HAS_D, bool HAS_O>
+int launch_llg_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
+    const LlgMarchGeom g = llg_march_geometry(p, true, g_dxdt == nullptr);
+    if (g.n_int_items > 0) {
+        auto lean = llg_march_vjp_kernel<HAS_D, HAS_O, PART_LEAN>;
+        lean<<<llg_march_grid(lean, g.n_int_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    }
+    auto rest = llg_march_vjp_kernel<HAS_D, HAS_O, PART_REST>;
+    rest<<<llg_march_grid(rest, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    return check_launch("dpde_guidance_vjp (llg march)");
+}
+
 int launch_llg_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal,
                       float* trace, cudaStream_t s) {
+    if (llg_march_wanted(p)) {
+        const bool d = p.dxdt.p != nullptr, o = p.has_u != 0;
+        return d ? (o ? launch_llg_march_reduce<true, true>(p, partials, ticket, sums, finalize, scal, trace, s)
+                      : launch_llg_march_reduce<true, false>(p, partials, ticket, sums, finalize, scal, trace, s))
+                 : (o ? launch_llg_march_reduce<false, true>(p, partials, ticket, sums, finalize, scal, trace, s)
+                      : launch_llg_march_reduce<false, false>(p, partials, ticket, sums, finalize, scal, trace, s));
+    }
     const LlgGeom L = llg_geometry(p);
     if (p.kind == DPDE_PDE_LLG_NORM) {
         auto k = llg_norm_reduce_kernel;
@@ -973,6 +1123,11 @@ int launch_llg_reduce(const Params& p, double* partials, unsigned int* ticket, d
 }
 
 int launch_llg_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
+    if (llg_march_wanted(p)) {
+        const bool d = p.dxdt.p != nullptr, o = p.has_u != 0;
+        return d ? (o ? launch_llg_march_vjp<true, true>(p, scal, upstream, g_x0, g_dxdt, s) : launch_llg_march_vjp<true, false>(p, scal, upstream, g_x0, g_dxdt, s))
+                 : (o ? launch_llg_march_vjp<false, true>(p, scal, upstream, g_x0, g_dxdt, s) : launch_llg_march_vjp<false, false>(p, scal, upstream, g_x0, g_dxdt, s));
+    }
     const LlgGeom L = llg_geometry(p);
     if (p.kind == DPDE_PDE_LLG_NORM) {
         auto k = llg_norm_vjp_kernel;
@@ -1009,20 +1164,15 @@ inline int64_t per_sample_item_bound(int B, int Cu, int H, int W) {
 template <bool HAS_D>
 int launch_march_per_sample_reduce(const Params& p, double* partials, double* out, cudaStream_t s) {
     const MarchGeom g = march_geometry(p, false);
-    constexpr int smem = ring_bytes(0, false);
-    auto k = heat_march_reduce_kernel<HAS_D, false, 0, true>;
-    k<<<march_grid(k, g, smem, true), kThreads, smem, s>>>(p, g, partials, nullptr, nullptr, 0, nullptr, nullptr);
+    if (int rc = launch_march_reduce_parts<HAS_D, false, 0, true>(p, g, partials, nullptr, nullptr, 0, nullptr, nullptr, s)) return rc;
     per_sample_items_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(partials, g.n_seg_items / p.B, p.B, out);
     return check_launch("dpde_heat_residual_sq (march)");
 }
 
 template <bool HAS_D>
 int launch_march_per_sample_vjp(const Params& p, const double* upstream, float* g_u, float* g_dudt, cudaStream_t s) {
-    const MarchGeom g = march_geometry(p, true);
-    constexpr int smem = ring_bytes(0, true);
-    auto k = heat_march_vjp_kernel<HAS_D, false, 0, true>;
-    k<<<march_grid(k, g, smem, true), kThreads, smem, s>>>(p, g, nullptr, upstream, g_u, g_dudt);
-    return check_launch("dpde_heat_residual_sq_vjp (march)");
+    const MarchGeom g = march_geometry(p, true, g_dudt == nullptr);
+    return launch_march_vjp_parts<HAS_D, false, 0, true>(p, g, nullptr, upstream, g_u, g_dudt, s);
 }
 
 View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }

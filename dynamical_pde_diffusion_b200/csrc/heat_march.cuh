@@ -33,8 +33,14 @@ struct MarchGeom {
     int a_blocks_per_plane, n_a_items;   // a-plane work: blocks of kABlock float4 within one plane's owned rows
     int a_plane4;                        // float4 per a-plane (owned rows)
     int a_block4;                        // float4 per a-plane work item (kABlock, smaller on small problems)
-    int lean;                            // 1: interior work items take the lean loops (0 only via dpde_set_tuning, for A/B runs)
+    // interior rectangle of u work items (strips s_lo..s_hi x chunks c_lo..c_hi, empty when n_int_items == 0): full chunks
+    // whose rows (+ the stencil margin) lie inside grid and buffer, strips without an edge column.  They run in their own
+    // LEAN kernel; everything else (and the a-planes) in the REST kernel -- see "Three kernels" below.
+    int s_lo, s_hi, c_lo, c_hi, n_int_items;
+    int part_base;                       // REST kernel: first per-CTA partial slot it owns (= grid of the LEAN kernel)
 };
+
+enum { PART_ALL = 0, PART_LEAN = 1, PART_REST = 2 };
 
 constexpr int kABlock = 1024;            // largest a-plane work item, in float4 (4096 pixels)
 
@@ -47,6 +53,8 @@ __device__ __forceinline__ uchar4 ldg4(const unsigned char* p) { return __ldg(re
 // (PA == 1; PA == 2: mask_a empty, nothing to read, ring as PA = 0) ride in the same ring element -- 4 deep, 90112 B.
 // The reduce pass carries no residual window and no output pointers: it fits 80 registers, so with a 4-deep ring
 // (53 KB) THREE CTAs share an SM (24 warps instead of 16) -- it is issue-bound, not bandwidth-bound.
+constexpr int kLeanRing = 8;             // rows per lane in flight in the LEAN kernels
+__host__ __device__ constexpr int lean_ring_bytes() { return kLeanRing * kThreads * (3 * 16 + 4); }
 __host__ __device__ constexpr int ring_depth(int PA, bool vjp) { return (PA == 1 || !vjp) ? 4 : 8; }
 __host__ __device__ constexpr int ring_bytes(int PA, bool vjp) { return ring_depth(PA, vjp) * kThreads * (PA == 1 ? 5 * 16 + 2 * 4 : 3 * 16 + 4); }
 
@@ -120,7 +128,7 @@ struct D4v {
 __device__ __forceinline__ D4v widen(const float4& f) { return D4v{{(double)f.x, (double)f.y, (double)f.z, (double)f.w}}; }
 
 struct MarchLane {
-    int b, cu, col0, ys, ye;
+    int b, cu, col0, ys, ye, strip, chunk;
     bool lane_ok, out_ok, left_edge, right_edge;
 };
 
@@ -143,6 +151,8 @@ __device__ __forceinline__ MarchLane march_decode(const Params& p, const MarchGe
     m.right_edge = (m.col0 + 4 == p.W);
     m.ys = p.ylo + (int)chunk * g.R;
     m.ye = min(m.ys + g.R, p.yhi);
+    m.strip = strip;
+    m.chunk = (int)chunk;
     return m;
 }
 
@@ -348,95 +358,57 @@ __device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// pass 1 (fast): S_a, S_u, S_pde
+// Three kernels per pass (round 2).  The lean interior loop and the general loop must not share a kernel: inlined side by
+// side they spilled inside both loops (80-register reduce kernel: 0.394 ms instead of 0.336 ms), and as __noinline__
+// functions the general loop and the a-plane streaming read the parameter block through a generic pointer -- ncu showed
+// integer instructions waiting on the long scoreboard for p.* loads (VJP: 1.13 ms).  So the host launches
+//   PART_LEAN  the interior rectangle of u work items, lean loop only (no a-planes, no epilogue: per-CTA partial -> slot),
+//   PART_REST  the remaining u items with the general loop + all a-plane items + the reduction epilogue over BOTH
+//              kernels' partial slots (stream order makes the LEAN kernel's slots final),
+// or, when the rectangle is empty (narrow or small grids, tuning key 5), the single PART_ALL kernel of round 1.
 // ---------------------------------------------------------------------------------------------------------
-// Register hygiene (round 2): the kernel body holds only the work-item loop and the LEAN interior loop.  The general
-// u-item loop (reflecting loader, edge selects, per-row validity, paired a-planes) and the a-plane streaming items are
-// __noinline__ device functions with their own register allocation -- inlined next to the lean loop they pushed the
-// 80-register reduce kernel into local-memory spills inside BOTH loops (measured: 0.394 ms instead of 0.336 ms).
 struct Sums3 {
     double a, u, p;
 };
 
 // Is every row of [first, last] inside the local buffer and inside the global grid (no reflection, no clamp)?
-__device__ __forceinline__ bool rows_inside(const Params& p, int first, int last) {
+__host__ __device__ __forceinline__ bool rows_inside(const Params& p, int first, int last) {
     return first >= 0 && last <= p.H - 1 && first + p.yg0 >= 0 && last + p.yg0 <= p.Hg - 1;
 }
 
-// General u-item of the reduce pass (any geometry).  Returns the item's contributions; in per-sample mode (PS) the
-// caller writes .p to partials.  Iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j],
-// uc = u[j+1]; ring element s is row ys + s: uc comes from element it+1, dudt / obs / mask from element it.
-template <bool HAS_D, bool HAS_O, int PA>
-__device__ __noinline__ Sums3 march_reduce_general(const Params& p, const MarchGeom& g, int wi, unsigned char* ring_mem) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int LW = 1 << g.lw_log2;
-    RowRing<HAS_D, HAS_O, PA, false> ring;
-    constexpr int kRing = ring_depth(PA, false);
-    ring.init(ring_mem, tid);
-    const MarchLane m = march_decode(p, g, wi, lane);
-    ring.bind(p, m, reinterpret_cast<const float*>(p.x0.p), reinterpret_cast<const float*>(p.dxdt.p));
-    const int n_it = g.R, n_el = g.R + 1;
-    ring.begin_item(p, m.ys, n_el - 1);
-    const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
-    double s_a = 0.0, s_u = 0.0, s_p = 0.0;
-#pragma unroll
-    for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
-    D4v ua = widen(ring.direct_u(p, m.ys - 1)), ub = widen(ring.direct_u(p, m.ys));
-#pragma unroll 2
-    for (int it = 0; it < n_it; ++it) {
-        cp_async_wait<kRing - 2>();                          // elements <= it + 1 have landed
-        const D4v uc = widen(ring.get_u(it + 1));
-        const float4 dt = ring.get_d(it), o = ring.get_o(it);
-        unsigned k = ring.get_m(it);
-        float4 av, oav;
-        unsigned ka = 0u;
-        if (PA == 1) {
-            av = ring.get_a(it);
-            oav = ring.get_oa(it);
-            ka = ring.get_ma(it);
-        }
-        const int sn = it + kRing;                           // refill the slot just drained
-        ring.issue(p, sn, sn < n_el, sn < n_it, sn < n_it);
-        double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
-        if (m.left_edge) lf = ub.v[1];                       // reflect: u[-1] = u[1]
-        if (m.right_edge) rt = ub.v[2];
-        const bool ok = m.out_ok && m.ys + it < m.ye;
-        double s[4];
-        lap_row(ua, ub, uc, lf, rt, s);
-        const double r0 = (double)dt.x - a_s * s[0], r1 = (double)dt.y - a_s * s[1];
-        const double r2 = (double)dt.z - a_s * s[2], r3 = (double)dt.w - a_s * s[3];
-        const double okf = ok ? 1.0 : 0.0;
-        s_p += okf * ((r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3));
-        if (HAS_O) {
-            if (!ok) k = 0u;
-            const double d0 = u8_to_double(k & 255u) * (ub.v[0] - (double)o.x), d1 = u8_to_double((k >> 8) & 255u) * (ub.v[1] - (double)o.y);
-            const double d2 = u8_to_double((k >> 16) & 255u) * (ub.v[2] - (double)o.z), d3 = u8_to_double(k >> 24) * (ub.v[3] - (double)o.w);
-            s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        }
-        if (PA == 1) {   // paired a-plane row: sum (mask (a - obs))^2
-            if (!ok) ka = 0u;
-            const double d0 = u8_to_double(ka & 255u) * ((double)av.x - (double)oav.x), d1 = u8_to_double((ka >> 8) & 255u) * ((double)av.y - (double)oav.y);
-            const double d2 = u8_to_double((ka >> 16) & 255u) * ((double)av.z - (double)oav.z), d3 = u8_to_double(ka >> 24) * ((double)av.w - (double)oav.w);
-            s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        }
-        ua = ub;
-        ub = uc;
-    }
-    cp_async_wait<0>();
-    return Sums3{s_a, s_u, s_p};
+__device__ __forceinline__ bool in_interior(const MarchGeom& g, int strip, int chunk) {
+    return g.n_int_items > 0 && strip >= g.s_lo && strip <= g.s_hi && chunk >= g.c_lo && chunk <= g.c_hi;
 }
 
-__device__ __noinline__ double a_item_reduce_call(const Params& p, const MarchGeom& g, int item) {
-    double s_a = 0.0;
-    a_item_reduce(p, g, item, threadIdx.x & 31, s_a);
-    return s_a;
+// LEAN kernel: interior item index -> lane geometry (all 32 lanes valid output-or-halo lanes of one strip)
+struct LeanItem {
+    int b, cu, col0, ys, si;             // si: index of the item in the general (b, unit, strip, chunk) ordering
+    bool out_ok;
+};
+__device__ __forceinline__ LeanItem lean_decode(const Params& p, const MarchGeom& g, int idx, int lane) {
+    LeanItem m;
+    unsigned t = (unsigned)idx / (unsigned)p.B;
+    m.b = (int)((unsigned)idx - t * p.B);
+    unsigned t2 = t / (unsigned)p.n_u_units;
+    m.cu = (int)(t - t2 * p.n_u_units);
+    const unsigned ns = (unsigned)(g.s_hi - g.s_lo + 1);
+    const unsigned cc = t2 / ns;
+    const int strip = g.s_lo + (int)(t2 - cc * ns), chunk = g.c_lo + (int)cc;
+    m.col0 = strip * g.strip_w - 4 * g.halo_lane + 4 * lane;
+    m.out_ok = m.col0 >= strip * g.strip_w && m.col0 < (strip + 1) * g.strip_w;
+    m.ys = p.ylo + chunk * g.R;
+    m.si = m.b + p.B * (m.cu + p.n_u_units * (strip + g.strips * chunk));
+    return m;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// pass 1 (fast): S_a, S_u, S_pde
+// ---------------------------------------------------------------------------------------------------------
 // PS (per-sample mode, training loss models/loss.py:143): no global sums -- every row-segment item writes its own
 // sum of squared residuals to partials[item] (items of sample b are b, b + B, b + 2 B, ...: per_sample_items_kernel adds
 // them in that order), nothing else is touched.
-template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
-__global__ void __launch_bounds__(kThreads, 3)
+template <bool HAS_D, bool HAS_O, int PA, bool PS = false, int PART = PART_ALL>
+__global__ void __launch_bounds__(kThreads, PART == PART_LEAN ? 2 : 3)
 heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g,
                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
                          int finalize, double* __restrict__ scal, float* __restrict__ trace) {
@@ -446,69 +418,63 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31;
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
-    using R_ = RowRing<HAS_D, HAS_O, 0, false>;
-    constexpr int kRing = ring_depth(PA, false);
-    constexpr unsigned F16 = kRing * kThreads * 16;
-    const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;   // RowRing::init's layout
-    const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
 
-    auto do_a = [&](int item) { s_a += a_item_reduce_call(p, g, item); };
-
-    auto do_u = [&](int wi) {
-        const MarchLane m = march_decode(p, g, wi, lane);
-        const int n_it = g.R;
-        // interior item (see the note above static_for): full chunk, every row ys-1 .. ys+R inside grid and buffer, no
-        // lane on an edge column, chunk length a multiple of the ring depth.  One unconditional vote by all 32 lanes:
-        // lanes of different row segments may disagree on the per-lane part.
-        const bool interior = __all_sync(0xffffffffu, PA == 0 && g.lean && (n_it & (kRing - 1)) == 0 && m.ye - m.ys == n_it &&
-                                                          rows_inside(p, m.ys - 1, m.ys + n_it) && m.lane_ok && !m.left_edge && !m.right_edge);
-        double item_p;
-        if (interior) {
-            const int W = p.W;
+    if constexpr (PART == PART_LEAN) {
+        // ---- interior items only: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1];
+        //      ring element s is row ys + s: uc comes from element it+1, dudt / obs / mask from element it.
+        constexpr int RD = kLeanRing;                                  // 8 rows per lane in flight (the lean loop retires a row
+        constexpr unsigned F16 = RD * kThreads * 16;                   // in ~90 instructions: 2 rows of lead exposed the HBM latency)
+        const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;
+        const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
+        auto slot16 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); };
+        auto slot4 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); };
+        const int W = p.W, n_it = g.R;
+        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
+            const LeanItem m = lean_decode(p, g, idx, lane);
             const int ch = p.ch_a + m.cu;
-            // running row pointers (lane's column included): ring element 0 = row ys
-            const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + m.col0 + (int64_t)m.ys * W;
-            const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + m.col0 + (int64_t)m.ys * W : nullptr;
-            const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + m.col0 + (int64_t)m.ys * W : nullptr;
-            const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + m.col0 + (int64_t)m.ys * W : nullptr;
+            const int64_t first = (int64_t)m.ys * W + m.col0;          // running row pointers (lane's column included)
+            const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + first;
+            const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + first : nullptr;
+            const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + first : nullptr;
+            const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + first : nullptr;
             const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
             D4v ua = widen(ldg4(pu - W)), ub = widen(ldg4(pu));
-            static_for<kRing>([&](auto J) {                               // prologue: elements 0 .. RD-1 (u of element 0 is ub)
+            static_for<RD>([&](auto J) {                               // prologue: elements 0 .. RD-1 (u of element 0 is ub)
                 constexpr int j = decltype(J)::value;
-                if (j >= 1) cp_async16(su + R_::slot16(j), pu + j * W);
-                if (HAS_D) cp_async16(sd + R_::slot16(j), pd + j * W);
+                if (j >= 1) cp_async16(su + slot16(j), pu + j * W);
+                if (HAS_D) cp_async16(sd + slot16(j), pd + j * W);
                 if (HAS_O) {
-                    cp_async16(so + R_::slot16(j), po + j * W);
-                    cp_async4(sm + R_::slot4(j), pm + j * W);
+                    cp_async16(so + slot16(j), po + j * W);
+                    cp_async4(sm + slot4(j), pm + j * W);
                 }
                 cp_async_commit();
             });
             double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
-            auto group = [&](auto TAIL) {                                 // RD row iterations; refills elements e0 + RD + j
+            auto group = [&](auto TAIL) {                              // RD row iterations; refills elements e0 + RD + j
                 constexpr bool tail = decltype(TAIL)::value;
-                pu += kRing * W;
-                if (HAS_D) pd += kRing * W;
-                if (HAS_O) { po += kRing * W; pm += kRing * W; }
-                static_for<kRing>([&](auto J) {
+                pu += RD * W;
+                if (HAS_D) pd += RD * W;
+                if (HAS_O) { po += RD * W; pm += RD * W; }
+                static_for<RD>([&](auto J) {
                     constexpr int j = decltype(J)::value;
-                    cp_async_wait<kRing - 2>();                           // elements <= it + 1 have landed
-                    const D4v uc = widen(lds128(su + R_::slot16(j + 1)));
-                    const float4 dt = HAS_D ? lds128(sd + R_::slot16(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cp_async_wait<RD - 2>();                           // elements <= it + 1 have landed
+                    const D4v uc = widen(lds128(su + slot16(j + 1)));
+                    const float4 dt = HAS_D ? lds128(sd + slot16(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     unsigned k = 0u;
                     if (HAS_O) {
-                        o = lds128(so + R_::slot16(j));
-                        k = lds32(sm + R_::slot4(j));
+                        o = lds128(so + slot16(j));
+                        k = lds32(sm + slot4(j));
                     }
-                    if (!tail) {                                          // element it + RD -> the slot just drained
-                        cp_async16(su + R_::slot16(j), pu + j * W);
-                        if (HAS_D) cp_async16(sd + R_::slot16(j), pd + j * W);
+                    if (!tail) {                                       // element it + RD -> the slot just drained
+                        cp_async16(su + slot16(j), pu + j * W);
+                        if (HAS_D) cp_async16(sd + slot16(j), pd + j * W);
                         if (HAS_O) {
-                            cp_async16(so + R_::slot16(j), po + j * W);
-                            cp_async4(sm + R_::slot4(j), pm + j * W);
+                            cp_async16(so + slot16(j), po + j * W);
+                            cp_async4(sm + slot4(j), pm + j * W);
                         }
-                    } else if (j == 0) {                                  // last group: only u of element n_it is still needed
-                        cp_async16(su + R_::slot16(j), pu + j * W);
+                    } else if (j == 0) {                               // last group: only u of element n_it is still needed
+                        cp_async16(su + slot16(j), pu + j * W);
                     }
                     cp_async_commit();
                     const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
@@ -520,7 +486,7 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
                     sp1 = fma(r1, r1, sp1);
                     sp0 = fma(r2, r2, sp0);
                     sp1 = fma(r3, r3, sp1);
-                    if (HAS_O) {                                          // mask in {0, 1}: (mask (u - obs))^2 = mask ? (u - obs)^2 : 0
+                    if (HAS_O) {                                       // mask in {0, 1}: (mask (u - obs))^2 = mask ? (u - obs)^2 : 0
                         const double d0 = ub.v[0] - (double)o.x, d1 = ub.v[1] - (double)o.y;
                         const double d2 = ub.v[2] - (double)o.z, d3 = ub.v[3] - (double)o.w;
                         fma_if<0>(su0, d0, d0, k);
@@ -532,152 +498,115 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
                     ub = uc;
                 });
             };
-            const int groups = n_it / kRing;
+            const int groups = n_it / RD;
 #pragma unroll 1
             for (int gi = 0; gi < groups - 1; ++gi) group(std::false_type{});
             group(std::true_type{});
             cp_async_wait<0>();
-            item_p = m.out_ok ? sp0 + sp1 : 0.0;                          // halo lanes computed on neighbouring columns: dropped here
+            const double item_p = m.out_ok ? sp0 + sp1 : 0.0;          // halo lanes computed on neighbouring columns: dropped here
             if (m.out_ok) s_u += su0 + su1;
-        } else {
-            const Sums3 r = march_reduce_general<HAS_D, HAS_O, PA>(p, g, wi, ring_mem);
-            s_a += r.a;
-            s_u += r.u;
-            item_p = r.p;
+            if (PS) {
+                double v = item_p;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) partials[m.si] = v;
+            } else {
+                s_p += item_p;
+            }
         }
+        if (PS) return;
+        block_sum3(s_a, s_u, s_p, scratch);                            // per-CTA partial -> slot; the REST kernel's last CTA adds them
+        if (tid == 0) {
+            partials[3 * blockIdx.x + 0] = 0.0;
+            partials[3 * blockIdx.x + 1] = s_u;
+            partials[3 * blockIdx.x + 2] = s_p;
+        }
+        return;
+    } else {
+    const float* x0 = reinterpret_cast<const float*>(p.x0.p);
+    const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
+
+    // ---- a-planes: sum (mask (a - obs))^2; a warp streams one block of a plane with 128-bit loads
+    auto do_a = [&](int item) { a_item_reduce(p, g, item, lane, s_a); };
+
+    // ---- u-planes: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1].
+    //      Ring element s is row ys + s:  uc comes from element it+1, dudt / obs / mask from element it.
+    const int LW = 1 << g.lw_log2;
+    RowRing<HAS_D, HAS_O, PA, false> ring;
+    constexpr int kRing = ring_depth(PA, false);
+    ring.init(ring_mem, tid);
+    auto do_u = [&](int wi) {
+        const MarchLane m = march_decode(p, g, wi, lane);
+        if (PART == PART_REST && in_interior(g, m.strip, m.chunk)) return;   // the LEAN kernel's item (warp-uniform: one segment per warp)
+        ring.bind(p, m, x0, dxp);
+        const int n_it = g.R, n_el = g.R + 1;
+        ring.begin_item(p, m.ys, n_el - 1);
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 1 && s < n_el, s < n_it, s < n_it);
+        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
+        D4v ua = widen(ring.direct_u(p, m.ys - 1)), ub = widen(ring.direct_u(p, m.ys));
+#pragma unroll 3
+        for (int it = 0; it < n_it; ++it) {
+            cp_async_wait<kRing - 2>();                          // elements <= it + 1 have landed
+            const D4v uc = widen(ring.get_u(it + 1));
+            const float4 dt = ring.get_d(it), o = ring.get_o(it);
+            unsigned k = ring.get_m(it);
+            float4 av, oav;
+            unsigned ka = 0u;
+            if (PA == 1) {
+                av = ring.get_a(it);
+                oav = ring.get_oa(it);
+                ka = ring.get_ma(it);
+            }
+            const int sn = it + kRing;                           // refill the slot just drained
+            ring.issue(p, sn, sn < n_el, sn < n_it, sn < n_it);
+            double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
+            if (m.left_edge) lf = ub.v[1];                       // reflect: u[-1] = u[1]
+            if (m.right_edge) rt = ub.v[2];
+            const bool ok = m.out_ok && m.ys + it < m.ye;
+            double s[4];
+            lap_row(ua, ub, uc, lf, rt, s);
+            const double r0 = (double)dt.x - a_s * s[0], r1 = (double)dt.y - a_s * s[1];
+            const double r2 = (double)dt.z - a_s * s[2], r3 = (double)dt.w - a_s * s[3];
+            const double okf = ok ? 1.0 : 0.0;
+            s_p += okf * ((r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3));
+            if (HAS_O) {
+                if (!ok) k = 0u;
+                const double d0 = u8_to_double(k & 255u) * (ub.v[0] - (double)o.x), d1 = u8_to_double((k >> 8) & 255u) * (ub.v[1] - (double)o.y);
+                const double d2 = u8_to_double((k >> 16) & 255u) * (ub.v[2] - (double)o.z), d3 = u8_to_double(k >> 24) * (ub.v[3] - (double)o.w);
+                s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+            if (PA == 1) {   // paired a-plane row: sum (mask (a - obs))^2
+                if (!ok) ka = 0u;
+                const double d0 = u8_to_double(ka & 255u) * ((double)av.x - (double)oav.x), d1 = u8_to_double((ka >> 8) & 255u) * ((double)av.y - (double)oav.y);
+                const double d2 = u8_to_double((ka >> 16) & 255u) * ((double)av.z - (double)oav.z), d3 = u8_to_double(ka >> 24) * ((double)av.w - (double)oav.w);
+                s_a += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+            ua = ub;
+            ub = uc;
+        }
+        cp_async_wait<0>();
         if (PS) {   // segmented (LW-lane) butterfly, lane 0 of every segment owns the item's sum
-            const int LW = 1 << g.lw_log2;
-            double v = item_p;
+            double v = s_p;
             for (int o = LW >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LW);
             const unsigned si = (unsigned)wi * g.segs_per_warp + (lane >> g.lw_log2);
             if ((lane & (LW - 1)) == 0 && si < (unsigned)g.n_seg_items) partials[si] = v;
-        } else {
-            s_p += item_p;
+            s_p = 0.0;
         }
     };
     run_interleaved(warp0, nwarps, g.n_warp_items, (PA == 0 && p.has_a) ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
     if (PS) return;
 
-    reduce_epilogue(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
+    // this kernel's slots start at part_base (0 unless a LEAN kernel ran first); the last CTA adds ALL slots in index order
+    reduce_epilogue_n<kThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace, g.part_base);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // pass 2 (fast): seed gradient
 // ---------------------------------------------------------------------------------------------------------
-// General u-item of the VJP (any geometry).  Iteration `it` computes the residual of row j = ys - 1 + it (window
-// ua = u[j-1], ub = u[j], uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo],
-// r0 = r[jo+1].  Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
-template <bool HAS_D, bool HAS_O, int PA>
-__device__ __noinline__ void march_vjp_general(const Params& p, const MarchGeom& g, int wi, unsigned char* ring_mem, double c_a, double c_u,
-                                               double c_p, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int LW = 1 << g.lw_log2;
-    const int64_t plane = (int64_t)p.H * p.W;
-    RowRing<HAS_D, HAS_O, PA, true> ring;
-    constexpr int kRing = ring_depth(PA, true);
-    ring.init(ring_mem, tid);
-    const MarchLane m = march_decode(p, g, wi, lane);
-    ring.bind(p, m, reinterpret_cast<const float*>(p.x0.p), reinterpret_cast<const float*>(p.dxdt.p));
-    const int n_it = g.R + 2;
-    ring.begin_item(p, m.ys - 2, n_it + 1);
-    // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
-#pragma unroll
-    for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
-    const int ch = p.ch_a + m.cu, colc = ring.colc;
-    float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane;                                   // (+ colc at the store)
-    float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane : nullptr;
-    float* gaout = PA ? g_x0 + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;                 // paired a-plane
-    float* gadout = (PA && g_dxdt) ? g_dxdt + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;
-    const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
-    const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
-    D4v ua = widen(ring.direct_u(p, m.ys - 2)), ub = widen(ring.direct_u(p, m.ys - 1));
-    double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
-    for (int it = 0; it < n_it; ++it) {
-        const int j = m.ys - 1 + it;
-        cp_async_wait<kRing - 3>();                          // elements <= it + 2 have landed
-        const D4v uc = widen(ring.get_u(it + 2));
-        const float4 dt = ring.get_d(it + 1), o = ring.get_o(it);
-        const unsigned k = ring.get_m(it);
-        float4 av, oav;
-        unsigned ka = 0u;
-        if (PA == 1) {
-            av = ring.get_a(it);
-            oav = ring.get_oa(it);
-            ka = ring.get_ma(it);
-        }
-        const int sn = it + kRing;
-        ring.issue(p, sn, sn < n_it + 2, sn < n_it + 1, sn < n_it);
-        double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
-        if (m.left_edge) lf = ub.v[1];
-        if (m.right_edge) rt = ub.v[2];
-        // r of rows outside the grid and of idle lanes is garbage (finite: it is computed from real, clamped
-        // data); it is never consumed: the vertical weights below vanish for out-of-grid neighbours and the
-        // edge lanes zero their horizontal neighbour.
-        double s[4], r0[4];
-        lap_row(ua, ub, uc, lf, rt, s);
-        r0[0] = (double)dt.x - a_s * s[0];
-        r0[1] = (double)dt.y - a_s * s[1];
-        r0[2] = (double)dt.z - a_s * s[2];
-        r0[3] = (double)dt.w - a_s * s[3];
-
-        double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1, LW), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1, LW);
-        if (m.left_edge) l1 = 0.0;
-        if (m.right_edge) q1 = 0.0;
-        const int jo = j - 1;
-        if (it >= 2 && jo < m.ye && m.out_ok) {
-            const int gjo = jo + p.yg0;
-            // transposed-stencil weights of the rows above / below: 2 from a boundary row, 0 from outside
-            const double wu = gjo == 0 ? 0.0 : (gjo == 1 ? 2.0 : 1.0);
-            const double wd = gjo == p.Hg - 1 ? 0.0 : (gjo == p.Hg - 2 ? 2.0 : 1.0);
-            const double a0 = ((wu * r2[0] + wd * r0[0]) + (l1 + r1[1])) - 4.0 * r1[0];
-            const double a1 = ((wu * r2[1] + wd * r0[1]) + (wl1 * r1[0] + r1[2])) - 4.0 * r1[1];
-            const double a2 = ((wu * r2[2] + wd * r0[2]) + (r1[1] + wr2 * r1[3])) - 4.0 * r1[2];
-            const double a3 = ((wu * r2[3] + wd * r0[3]) + (r1[2] + q1)) - 4.0 * r1[3];
-            double v0 = kp * a0, v1 = kp * a1, v2 = kp * a2, v3 = kp * a3;
-            if (HAS_O) {   // ua is u[jo]
-                const double m0 = u8_to_double(k & 255u), m1 = u8_to_double((k >> 8) & 255u), m2 = u8_to_double((k >> 16) & 255u), m3 = u8_to_double(k >> 24);
-                v0 += c_u * (m0 * (m0 * (ua.v[0] - (double)o.x)));
-                v1 += c_u * (m1 * (m1 * (ua.v[1] - (double)o.y)));
-                v2 += c_u * (m2 * (m2 * (ua.v[2] - (double)o.z)));
-                v3 += c_u * (m3 * (m3 * (ua.v[3] - (double)o.w)));
-            }
-            *reinterpret_cast<float4*>((gout + (int64_t)jo * p.W) + colc) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
-            if (gdout)
-                *reinterpret_cast<float4*>((gdout + (int64_t)jo * p.W) + colc) =
-                    make_float4((float)(c_p * r1[0]), (float)(c_p * r1[1]), (float)(c_p * r1[2]), (float)(c_p * r1[3]));
-            if (PA) {   // paired a-plane, row jo: g = c_a mask (mask (a - obs)); zeros when mask_a is empty
-                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (PA == 1) {
-                    const double m0 = u8_to_double(ka & 255u), m1 = u8_to_double((ka >> 8) & 255u), m2 = u8_to_double((ka >> 16) & 255u), m3 = u8_to_double(ka >> 24);
-                    w.x = (float)(c_a * (m0 * (m0 * ((double)av.x - (double)oav.x))));
-                    w.y = (float)(c_a * (m1 * (m1 * ((double)av.y - (double)oav.y))));
-                    w.z = (float)(c_a * (m2 * (m2 * ((double)av.z - (double)oav.z))));
-                    w.w = (float)(c_a * (m3 * (m3 * ((double)av.w - (double)oav.w))));
-                }
-                *reinterpret_cast<float4*>((gaout + (int64_t)jo * p.W) + colc) = w;
-                if (gadout) *reinterpret_cast<float4*>((gadout + (int64_t)jo * p.W) + colc) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            r2[i] = r1[i];
-            r1[i] = r0[i];
-        }
-        ua = ub;
-        ub = uc;
-    }
-    cp_async_wait<0>();
-}
-
-__device__ __noinline__ void a_item_vjp_call(const Params& p, const MarchGeom& g, int item, double c_a, float* __restrict__ g_x0,
-                                             float* __restrict__ g_dxdt) {
-    a_item_vjp(p, g, item, threadIdx.x & 31, c_a, g_x0, g_dxdt);
-}
-
 // PS (per-sample mode): `upstream` holds one seed per sample, c_p of an item = 2 upstream[b] (d r^2 / d r), no
 // observation terms, `scal` is not read.
-template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
+template <bool HAS_D, bool HAS_O, int PA, bool PS = false, int PART = PART_ALL>
 __global__ void __launch_bounds__(kThreads, 2)
 heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, const double* __restrict__ scal,
                       const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
@@ -685,116 +614,222 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     const int tid = threadIdx.x, lane = tid & 31;
     const double up = (!PS && upstream) ? __ldg(upstream) : 1.0;
     const double c_a = PS ? 0.0 : __ldg(scal + 4) * up, c_u = PS ? 0.0 : __ldg(scal + 5) * up;
-    const double c_p0 = PS ? 0.0 : __ldg(scal + 6) * up;
+    double c_p = PS ? 0.0 : __ldg(scal + 6) * up;
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
-    using R_ = RowRing<HAS_D, HAS_O, 0, true>;
-    constexpr int kRing = ring_depth(PA, true);
-    constexpr unsigned F16 = kRing * kThreads * 16;
-    const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;   // RowRing::init's layout
-    const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
 
-    auto do_a = [&](int item) { a_item_vjp_call(p, g, item, c_a, g_x0, g_dxdt); };
-
-    auto do_u = [&](int wi) {
-        const MarchLane m = march_decode(p, g, wi, lane);
-        const int n_it = g.R + 2;
-        const double c_p = PS ? 2.0 * __ldg(upstream + m.b) : c_p0;
-        // interior item (see the note above static_for): full chunk whose rows ys-2 .. ys+R+1 all lie inside grid and
-        // buffer (so no output row is one of the four rows with boundary weights), no lane on an edge column, no
-        // g_dxdt output, R + 2 a multiple of the ring depth.  One unconditional vote by all 32 lanes.
-        const bool interior = __all_sync(0xffffffffu, PA == 0 && g.lean && (n_it & (kRing - 1)) == 0 && n_it >= 2 * kRing && m.ye - m.ys == g.R &&
-                                                          !g_dxdt && rows_inside(p, m.ys - 2, m.ys + g.R + 1) && m.lane_ok && !m.left_edge && !m.right_edge);
-        if (!interior) {
-            march_vjp_general<HAS_D, HAS_O, PA>(p, g, wi, ring_mem, c_a, c_u, c_p, g_x0, g_dxdt);
-            return;
-        }
-        const int W = p.W;
-        const int ch = p.ch_a + m.cu;
-        const int64_t first = (int64_t)(m.ys - 2) * W + m.col0;           // ring element 0 = row ys - 2 (lane's column included)
-        const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + first;
-        const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + first : nullptr;
-        const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + first : nullptr;
-        const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + first : nullptr;
-        float* pg = g_x0 + ((int64_t)m.b * p.C + ch) * ((int64_t)p.H * W) + first;   // output row of iteration `it` is element it
-        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
-        D4v ua = widen(ldg4(pu)), ub = widen(ldg4(pu + W));
-        static_for<kRing>([&](auto J) {                               // prologue: u / obs of elements >= 2, dudt of elements >= 1
-            constexpr int j = decltype(J)::value;
-            if (j >= 2) cp_async16(su + R_::slot16(j), pu + j * W);
-            if (HAS_D && j >= 1) cp_async16(sd + R_::slot16(j), pd + j * W);
-            if (HAS_O && j >= 2) {
-                cp_async16(so + R_::slot16(j), po + j * W);
-                cp_async4(sm + R_::slot4(j), pm + j * W);
-            }
-            cp_async_commit();
-        });
-        double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
-        auto group = [&](auto TAIL, bool first_group) {
-            constexpr bool tail = decltype(TAIL)::value;
-            pu += kRing * W;
-            if (HAS_D) pd += kRing * W;
-            if (HAS_O) { po += kRing * W; pm += kRing * W; }
-            static_for<kRing>([&](auto J) {
+    if constexpr (PART == PART_LEAN) {
+        // ---- interior items only.  Iteration `it` computes the residual of row j = ys - 1 + it (window ua = u[j-1], ub = u[j],
+        //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
+        //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
+        constexpr int RD = kLeanRing;
+        constexpr unsigned F16 = RD * kThreads * 16;
+        const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;
+        const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
+        auto slot16 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); };
+        auto slot4 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); };
+        const int W = p.W, n_it = g.R + 2;
+        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
+            const LeanItem m = lean_decode(p, g, idx, lane);
+            const int ch = p.ch_a + m.cu;
+            if (PS) c_p = 2.0 * __ldg(upstream + m.b);
+            const int64_t first = (int64_t)(m.ys - 2) * W + m.col0;    // ring element 0 = row ys - 2 (lane's column included)
+            const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + first;
+            const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + first : nullptr;
+            const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + first : nullptr;
+            const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + first : nullptr;
+            float* pg = g_x0 + ((int64_t)m.b * p.C + ch) * ((int64_t)p.H * W) + first;   // output row of iteration `it` is element it
+            const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
+            D4v ua = widen(ldg4(pu)), ub = widen(ldg4(pu + W));
+            static_for<RD>([&](auto J) {                               // prologue: u / obs of elements >= 2, dudt of elements >= 1
                 constexpr int j = decltype(J)::value;
-                cp_async_wait<kRing - 3>();                           // elements <= it + 2 have landed
-                const D4v uc = widen(lds128(su + R_::slot16(j + 2)));
-                const float4 dt = HAS_D ? lds128(sd + R_::slot16(j + 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                unsigned k = 0u;
-                if (HAS_O) {
-                    o = lds128(so + R_::slot16(j));
-                    k = lds32(sm + R_::slot4(j));
-                }
-                if (!tail) {                                          // element it + RD -> the slot just drained
-                    cp_async16(su + R_::slot16(j), pu + j * W);
-                    if (HAS_D) cp_async16(sd + R_::slot16(j), pd + j * W);
-                    if (HAS_O) {
-                        cp_async16(so + R_::slot16(j), po + j * W);
-                        cp_async4(sm + R_::slot4(j), pm + j * W);
-                    }
-                } else {                                              // last group: u of elements n_it, n_it + 1; dudt of element n_it
-                    if (j <= 1) cp_async16(su + R_::slot16(j), pu + j * W);
-                    if (HAS_D && j == 0) cp_async16(sd + R_::slot16(j), pd + j * W);
+                if (j >= 2) cp_async16(su + slot16(j), pu + j * W);
+                if (HAS_D && j >= 1) cp_async16(sd + slot16(j), pd + j * W);
+                if (HAS_O && j >= 2) {
+                    cp_async16(so + slot16(j), po + j * W);
+                    cp_async4(sm + slot4(j), pm + j * W);
                 }
                 cp_async_commit();
-                const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
-                double sv[4], r0[4];
-                lap_row(ua, ub, uc, lf, rt, sv);
-                r0[0] = (double)dt.x - a_s * sv[0];
-                r0[1] = (double)dt.y - a_s * sv[1];
-                r0[2] = (double)dt.z - a_s * sv[2];
-                r0[3] = (double)dt.w - a_s * sv[3];
-                const double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1);
-                if ((j >= 2 || !first_group) && m.out_ok) {          // rows ys - 2, ys - 1 belong to the previous chunk
-                    // K^T r on an interior row / column: all weights are 1
-                    double v0 = kp * (((r2[0] + r0[0]) + (l1 + r1[1])) - 4.0 * r1[0]);
-                    double v1 = kp * (((r2[1] + r0[1]) + (r1[0] + r1[2])) - 4.0 * r1[1]);
-                    double v2 = kp * (((r2[2] + r0[2]) + (r1[1] + r1[3])) - 4.0 * r1[2]);
-                    double v3 = kp * (((r2[3] + r0[3]) + (r1[2] + q1)) - 4.0 * r1[3]);
-                    if (HAS_O) {                                      // mask in {0, 1}: c_u mask^2 (u - obs); ua is u of the output row
-                        fma_if<0>(v0, c_u, ua.v[0] - (double)o.x, k);
-                        fma_if<1>(v1, c_u, ua.v[1] - (double)o.y, k);
-                        fma_if<2>(v2, c_u, ua.v[2] - (double)o.z, k);
-                        fma_if<3>(v3, c_u, ua.v[3] - (double)o.w, k);
-                    }
-                    *reinterpret_cast<float4*>(pg + j * W) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    r2[i] = r1[i];
-                    r1[i] = r0[i];
-                }
-                ua = ub;
-                ub = uc;
             });
-            pg += kRing * W;
-        };
-        const int groups = n_it / kRing;
-        group(std::false_type{}, true);
+            double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
+            auto group = [&](auto TAIL, bool first_group) {
+                constexpr bool tail = decltype(TAIL)::value;
+                pu += RD * W;
+                if (HAS_D) pd += RD * W;
+                if (HAS_O) { po += RD * W; pm += RD * W; }
+                static_for<RD>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    cp_async_wait<RD - 3>();                           // elements <= it + 2 have landed
+                    const D4v uc = widen(lds128(su + slot16(j + 2)));
+                    const float4 dt = HAS_D ? lds128(sd + slot16(j + 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned k = 0u;
+                    if (HAS_O) {
+                        o = lds128(so + slot16(j));
+                        k = lds32(sm + slot4(j));
+                    }
+                    if (!tail) {                                       // element it + RD -> the slot just drained
+                        cp_async16(su + slot16(j), pu + j * W);
+                        if (HAS_D) cp_async16(sd + slot16(j), pd + j * W);
+                        if (HAS_O) {
+                            cp_async16(so + slot16(j), po + j * W);
+                            cp_async4(sm + slot4(j), pm + j * W);
+                        }
+                    } else {                                           // last group: u of elements n_it, n_it + 1; dudt of element n_it
+                        if (j <= 1) cp_async16(su + slot16(j), pu + j * W);
+                        if (HAS_D && j == 0) cp_async16(sd + slot16(j), pd + j * W);
+                    }
+                    cp_async_commit();
+                    const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
+                    double sv[4], r0[4];
+                    lap_row(ua, ub, uc, lf, rt, sv);
+                    r0[0] = (double)dt.x - a_s * sv[0];
+                    r0[1] = (double)dt.y - a_s * sv[1];
+                    r0[2] = (double)dt.z - a_s * sv[2];
+                    r0[3] = (double)dt.w - a_s * sv[3];
+                    const double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1);
+                    if ((j >= 2 || !first_group) && m.out_ok) {        // rows ys - 2, ys - 1 belong to the previous chunk
+                        // K^T r on an interior row / column: all weights are 1
+                        double v0 = kp * (((r2[0] + r0[0]) + (l1 + r1[1])) - 4.0 * r1[0]);
+                        double v1 = kp * (((r2[1] + r0[1]) + (r1[0] + r1[2])) - 4.0 * r1[1]);
+                        double v2 = kp * (((r2[2] + r0[2]) + (r1[1] + r1[3])) - 4.0 * r1[2]);
+                        double v3 = kp * (((r2[3] + r0[3]) + (r1[2] + q1)) - 4.0 * r1[3]);
+                        if (HAS_O) {                                   // mask in {0, 1}: c_u mask^2 (u - obs); ua is u of the output row
+                            fma_if<0>(v0, c_u, ua.v[0] - (double)o.x, k);
+                            fma_if<1>(v1, c_u, ua.v[1] - (double)o.y, k);
+                            fma_if<2>(v2, c_u, ua.v[2] - (double)o.z, k);
+                            fma_if<3>(v3, c_u, ua.v[3] - (double)o.w, k);
+                        }
+                        *reinterpret_cast<float4*>(pg + j * W) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        r2[i] = r1[i];
+                        r1[i] = r0[i];
+                    }
+                    ua = ub;
+                    ub = uc;
+                });
+                pg += RD * W;
+            };
+            const int groups = n_it / RD;
+            group(std::false_type{}, true);
 #pragma unroll 1
-        for (int gi = 1; gi < groups - 1; ++gi) group(std::false_type{}, false);
-        group(std::true_type{}, false);
+            for (int gi = 1; gi < groups - 1; ++gi) group(std::false_type{}, false);
+            group(std::true_type{}, false);
+            cp_async_wait<0>();
+        }
+        return;
+    } else {
+    const float* x0 = reinterpret_cast<const float*>(p.x0.p);
+    const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
+    const int64_t plane = (int64_t)p.H * p.W;
+
+    // ---- a-planes: g = c_a mask (mask (a - obs)), zeros when the mask is empty (sample.py:337-342)
+    auto do_a = [&](int item) { a_item_vjp(p, g, item, lane, c_a, g_x0, g_dxdt); };
+
+    // ---- u-planes.  Iteration `it` computes the residual of row j = ys - 1 + it (window ua = u[j-1], ub = u[j],
+    //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
+    //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
+    const int LW = 1 << g.lw_log2;
+    RowRing<HAS_D, HAS_O, PA, true> ring;
+    constexpr int kRing = ring_depth(PA, true);
+    ring.init(ring_mem, tid);
+    auto do_u = [&](int wi) {
+        const MarchLane m = march_decode(p, g, wi, lane);
+        if (PART == PART_REST && in_interior(g, m.strip, m.chunk)) return;   // the LEAN kernel's item
+        ring.bind(p, m, x0, dxp);
+        const int n_it = g.R + 2;
+        ring.begin_item(p, m.ys - 2, n_it + 1);
+        // fields of element s that are consumed: u for s in [2, n_it+2), dudt for s in [1, n_it+1), obs for s in [2, n_it)
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) ring.issue(p, s, s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
+        const int ch = p.ch_a + m.cu, colc = ring.colc;
+        float* gout = g_x0 + ((int64_t)m.b * p.C + ch) * plane;                                   // (+ colc at the store)
+        float* gdout = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + ch) * plane : nullptr;
+        float* gaout = PA ? g_x0 + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;                 // paired a-plane
+        float* gadout = (PA && g_dxdt) ? g_dxdt + ((int64_t)m.b * p.C + m.cu) * plane : nullptr;
+        if (PS) c_p = 2.0 * __ldg(upstream + m.b);
+        const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
+        const double wl1 = m.left_edge ? 2.0 : 1.0, wr2 = m.right_edge ? 2.0 : 1.0;   // transposed-stencil edge weights
+        D4v ua = widen(ring.direct_u(p, m.ys - 2)), ub = widen(ring.direct_u(p, m.ys - 1));
+        double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 3
+        for (int it = 0; it < n_it; ++it) {
+            const int j = m.ys - 1 + it;
+            cp_async_wait<kRing - 3>();                          // elements <= it + 2 have landed
+            const D4v uc = widen(ring.get_u(it + 2));
+            const float4 dt = ring.get_d(it + 1), o = ring.get_o(it);
+            const unsigned k = ring.get_m(it);
+            float4 av, oav;
+            unsigned ka = 0u;
+            if (PA == 1) {
+                av = ring.get_a(it);
+                oav = ring.get_oa(it);
+                ka = ring.get_ma(it);
+            }
+            const int sn = it + kRing;
+            ring.issue(p, sn, sn < n_it + 2, sn < n_it + 1, sn < n_it);
+            double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1, LW), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1, LW);
+            if (m.left_edge) lf = ub.v[1];
+            if (m.right_edge) rt = ub.v[2];
+            // r of rows outside the grid and of idle lanes is garbage (finite: it is computed from real, clamped
+            // data); it is never consumed: the vertical weights below vanish for out-of-grid neighbours and the
+            // edge lanes zero their horizontal neighbour.
+            double s[4], r0[4];
+            lap_row(ua, ub, uc, lf, rt, s);
+            r0[0] = (double)dt.x - a_s * s[0];
+            r0[1] = (double)dt.y - a_s * s[1];
+            r0[2] = (double)dt.z - a_s * s[2];
+            r0[3] = (double)dt.w - a_s * s[3];
+
+            double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1, LW), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1, LW);
+            if (m.left_edge) l1 = 0.0;
+            if (m.right_edge) q1 = 0.0;
+            const int jo = j - 1;
+            if (it >= 2 && jo < m.ye && m.out_ok) {
+                const int gjo = jo + p.yg0;
+                // transposed-stencil weights of the rows above / below: 2 from a boundary row, 0 from outside
+                const double wu = gjo == 0 ? 0.0 : (gjo == 1 ? 2.0 : 1.0);
+                const double wd = gjo == p.Hg - 1 ? 0.0 : (gjo == p.Hg - 2 ? 2.0 : 1.0);
+                const double a0 = ((wu * r2[0] + wd * r0[0]) + (l1 + r1[1])) - 4.0 * r1[0];
+                const double a1 = ((wu * r2[1] + wd * r0[1]) + (wl1 * r1[0] + r1[2])) - 4.0 * r1[1];
+                const double a2 = ((wu * r2[2] + wd * r0[2]) + (r1[1] + wr2 * r1[3])) - 4.0 * r1[2];
+                const double a3 = ((wu * r2[3] + wd * r0[3]) + (r1[2] + q1)) - 4.0 * r1[3];
+                double v0 = kp * a0, v1 = kp * a1, v2 = kp * a2, v3 = kp * a3;
+                if (HAS_O) {   // ua is u[jo]
+                    const double m0 = u8_to_double(k & 255u), m1 = u8_to_double((k >> 8) & 255u), m2 = u8_to_double((k >> 16) & 255u), m3 = u8_to_double(k >> 24);
+                    v0 += c_u * (m0 * (m0 * (ua.v[0] - (double)o.x)));
+                    v1 += c_u * (m1 * (m1 * (ua.v[1] - (double)o.y)));
+                    v2 += c_u * (m2 * (m2 * (ua.v[2] - (double)o.z)));
+                    v3 += c_u * (m3 * (m3 * (ua.v[3] - (double)o.w)));
+                }
+                *reinterpret_cast<float4*>((gout + (int64_t)jo * p.W) + colc) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+                if (gdout)
+                    *reinterpret_cast<float4*>((gdout + (int64_t)jo * p.W) + colc) =
+                        make_float4((float)(c_p * r1[0]), (float)(c_p * r1[1]), (float)(c_p * r1[2]), (float)(c_p * r1[3]));
+                if (PA) {   // paired a-plane, row jo: g = c_a mask (mask (a - obs)); zeros when mask_a is empty
+                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (PA == 1) {
+                        const double m0 = u8_to_double(ka & 255u), m1 = u8_to_double((ka >> 8) & 255u), m2 = u8_to_double((ka >> 16) & 255u), m3 = u8_to_double(ka >> 24);
+                        w.x = (float)(c_a * (m0 * (m0 * ((double)av.x - (double)oav.x))));
+                        w.y = (float)(c_a * (m1 * (m1 * ((double)av.y - (double)oav.y))));
+                        w.z = (float)(c_a * (m2 * (m2 * ((double)av.z - (double)oav.z))));
+                        w.w = (float)(c_a * (m3 * (m3 * ((double)av.w - (double)oav.w))));
+                    }
+                    *reinterpret_cast<float4*>((gaout + (int64_t)jo * p.W) + colc) = w;
+                    if (gadout) *reinterpret_cast<float4*>((gadout + (int64_t)jo * p.W) + colc) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r2[i] = r1[i];
+                r1[i] = r0[i];
+            }
+            ua = ub;
+            ub = uc;
+        }
         cp_async_wait<0>();
     };
     run_interleaved(warp0, nwarps, g.n_warp_items, PA == 0 ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+    }
 }

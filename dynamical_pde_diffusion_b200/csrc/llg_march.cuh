@@ -1,0 +1,513 @@
+// LLG m x H_eff residual, row-marching kernels (round 2): the design that took the heat kernels to the HBM roofline,
+// applied to the three-component magnetisation.
+//
+// Included by guidance.cu after llg_tile.cuh (inside namespace dpde::{anonymous}); uses Params / MarchGeom (a-plane
+// fields) / a_item_* / reduce_epilogue / row_offset / cp_async* / static_for / rows_inside / fma_if-style predicates.
+//
+// Why not the convert-once tiles of round 1 (llg_tile.cuh, kept for grids narrower than 128 columns): ncu of those kernels
+// on 8 x 6 x 2048^2 (profiles/r1k_large_llg_ncu_full_summary.txt + the per-instruction page) -- 277 (reduce) / 418 (VJP)
+// executed warp instructions per 32 pixels of which only 70 / 159 are fp64 arithmetic: per-thread cp.async address
+// arithmetic with divisions by 18 and 20, a separate convert pass, two CTA barriers per tile, a halo ring recomputed by
+// the first warps (16 % more residual evaluations, 43 % issue utilisation, 24 % of the warp slots occupied).  Marching:
+//   * a lane owns TWO adjacent columns and marches down the rows of its chunk; every magnetisation row is fetched once
+//     (cp.async, 8 bytes per lane and component, 256-byte coalesced warp rows) and widened once; the vertical stencil
+//     neighbours live in a three-row fp64 register window, the horizontal ones come from the adjacent lanes by shuffle;
+//   * the VJP keeps a second three-row window of the field gradient G_H = d loss / d H_eff and emits row j - 1 while it
+//     evaluates row j: K^T G_H needs no shared tile, no barrier and no recomputed ring (only the two halo lanes of a
+//     60-column strip repeat work: 6 %);
+//   * interior work items (full chunks away from the grid boundary, strips without an edge column) run a lean loop with
+//     compile-time ring slots and running row pointers in their own LEAN kernel; the rest runs the same loop with
+//     reflected row offsets, edge selects and per-row validity (template flag) in the REST kernel, together with the
+//     a-plane streaming items and the reduction epilogue -- see "Three kernels" in heat_march.cuh for the rationale;
+//   * the algebra is arranged for the fp64 pipe (the VJP needs ~100 fp64 instructions per pixel, as long as its 60 B of
+//     HBM traffic): r = dmdt + tau gamma a + tau alpha m x a;  with q = r x m and t = gamma r + alpha q:
+//     G_H = -gamma q - alpha q x m,  G_m = -(H x t) - alpha a x r;  the seed coefficient c_p multiplies the sums once.
+// Masks are 0 / 1 bytes (DPDE_U8): observation terms are predicated DFMAs.  Arithmetic and accumulation are fp64.
+//
+// Eligibility (host): as llg_tile.cuh (fp32 fields, W % 4 == 0, aligned bases, fp32 observations, uint8 masks) and W >= 128.
+
+constexpr int kLR = 4;                       // ring depth (rows per lane in flight)
+constexpr int kLlgThreads = 128;             // 4 warps per CTA: three CTAs share an SM at <= 170 registers
+constexpr int kLlgFields = 9;                // m[3], dmdt[3], obs[3] -- 8 bytes per lane and row each
+constexpr int kLlgStrip = 60;                // output columns per warp strip (+ one 2-column halo lane per side)
+__host__ __device__ constexpr int llg_ring_bytes() { return kLlgFields * kLR * kLlgThreads * 8; }
+
+struct LlgMarchGeom {
+    MarchGeom a;                             // a-plane streaming fields (a_plane4, a_block4, n_a_items, ...)
+    int strips, R, chunks, n_items;          // u work item = (b innermost, strip, chunk)
+    // interior rectangle (strips s_lo..s_hi x chunks c_lo..c_hi; n_int_items == 0: none) -> LEAN kernel, the rest -> REST
+    // kernel (heat_march.cuh, "Three kernels"); part_base: first partial slot of the REST kernel
+    int s_lo, s_hi, c_lo, c_hi, n_int_items, part_base;
+};
+
+struct LlgLane {
+    int b, col0, colc, ys, ye;
+    bool lane_ok, out_ok, left_edge, right_edge;
+};
+
+__device__ __forceinline__ bool llg_in_interior(const LlgMarchGeom& g, int strip, int chunk) {
+    return g.n_int_items > 0 && strip >= g.s_lo && strip <= g.s_hi && chunk >= g.c_lo && chunk <= g.c_hi;
+}
+
+// LEAN: `item` indexes the interior rectangle; otherwise the full (b, strip, chunk) space.  `skip`: REST kernel and the
+// item belongs to the LEAN kernel.
+template <bool LEAN>
+__device__ __forceinline__ LlgLane llg_lane_decode(const Params& p, const LlgMarchGeom& g, int item, int lane, bool& skip) {
+    LlgLane m;
+    const unsigned t = (unsigned)item / (unsigned)p.B;
+    m.b = (int)((unsigned)item - t * p.B);
+    const unsigned ns = LEAN ? (unsigned)(g.s_hi - g.s_lo + 1) : (unsigned)g.strips;
+    unsigned chunk = t / ns;
+    int strip = (int)(t - chunk * ns);
+    if (LEAN) {
+        strip += g.s_lo;
+        chunk += g.c_lo;
+    }
+    skip = !LEAN && llg_in_interior(g, strip, (int)chunk);
+    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
+    m.lane_ok = m.col0 >= 0 && m.col0 < p.W;
+    m.out_ok = m.lane_ok && lane >= 1 && lane <= 30;
+    m.colc = m.lane_ok ? m.col0 : 0;
+    m.left_edge = m.col0 == 0;
+    m.right_edge = m.col0 + 2 == p.W;
+    m.ys = p.ylo + (int)chunk * g.R;
+    m.ye = min(m.ys + g.R, p.yhi);
+    return m;
+}
+
+struct V6 {
+    double v[3][2];                          // [component][pixel of the lane]
+};
+
+__device__ __forceinline__ float2 lds64f(unsigned smem) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async8(unsigned smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ unsigned llg_slot(int field, int s) { return (unsigned)((field * kLR + (s & (kLR - 1))) * kLlgThreads * 8); }
+
+// acc = fma(a, b, acc) where `bit` is non-zero: a test + select of the 64-bit result (ptxas turns a predicated DFMA into
+// the same DFMA + FSEL pair)
+__device__ __forceinline__ void fma_where(double& acc, double a, double b, unsigned bit) {
+    const double r = fma(a, b, acc);
+    acc = bit ? r : acc;
+}
+
+// item constants
+struct LlgK {
+    double h[3];                             // applied field of the sample (A/m)
+    double kex;                              // c_ex / dx^2
+    double g1, g2;                           // tau gamma, tau alpha
+};
+
+// forward part at one pixel: H_eff, a = m x H, r
+__device__ __forceinline__ void llg_fwd_px(const Params& p, const LlgK& k, const double* m, const double* lap, const double* dt, double* H,
+                                           double* a, double* r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) H[c] = fma(k.kex, lap[c], k.h[c]);
+    if (p.c_an != 0.0) {
+        const double me = p.c_an * ((m[0] * p.e[0] + m[1] * p.e[1]) + m[2] * p.e[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[c] = fma(me, p.e[c], H[c]);
+    }
+    cross3(m, H, a);
+    double ma[3];
+    cross3(m, a, ma);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = fma(k.g2, ma[c], fma(k.g1, a[c], dt[c]));   // dmdt - tau (-gamma a - alpha m x a)
+}
+
+// backward part at one pixel for the UNSCALED seed s = r:  G_H = -gamma q - alpha q x m,  G_m = -(H x t) - alpha a x r
+// (+ the anisotropy path c_an (e . G_H) e), q = r x m, t = gamma r + alpha q.  d loss / d m = c_p (-tau) (G_m + ...) + ...
+__device__ __forceinline__ void llg_bwd_px(const Params& p, const double* m, const double* H, const double* a, const double* r, double* GH,
+                                           double* Gm) {
+    double q[3], qm[3], t[3], Ht[3], ar[3];
+    cross3(r, m, q);
+    cross3(q, m, qm);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        GH[c] = fma(-p.alpha, qm[c], -p.gamma * q[c]);
+        t[c] = fma(p.alpha, q[c], p.gamma * r[c]);
+    }
+    cross3(H, t, Ht);
+    cross3(a, r, ar);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Gm[c] = fma(-p.alpha, ar[c], -Ht[c]);
+    if (p.c_an != 0.0) {
+        const double eG = p.c_an * ((p.e[0] * GH[0] + p.e[1] * GH[1]) + p.e[2] * GH[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Gm[c] = fma(eG, p.e[c], Gm[c]);
+    }
+}
+
+// Per-lane state of one work item shared by the two passes.
+template <bool HAS_D, bool HAS_O>
+struct LlgRing {
+    unsigned base;                           // shared-window address of this lane's slot (field 0, slot 0)
+    const float* pm[3];                      // lane's column in the three magnetisation planes of the sample
+    const float* pd[3];
+    const float* po[3];
+    const unsigned char* pk[3];
+
+    __device__ __forceinline__ void bind(const Params& p, const LlgLane& m, unsigned char* smem) {
+        base = (unsigned)__cvta_generic_to_shared(smem) + threadIdx.x * 8;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            pm[c] = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)(p.ch_a + c) * p.x0.sc + m.colc;
+            pd[c] = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)(p.ch_a + c) * p.dxdt.sc + m.colc : nullptr;
+            po[c] = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)c * p.obs_u.sc + m.colc : nullptr;
+            pk[c] = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)c * p.mask_u.sc + m.colc : nullptr;
+        }
+    }
+    // start the copies of one ring element whose row starts at element offset `off` (row * W); always commits one group
+    __device__ __forceinline__ void issue(int s, int64_t off, bool fm, bool fd, bool fo) const {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (fm) cp_async8(base + llg_slot(c, s), pm[c] + off);
+            if (HAS_D && fd) cp_async8(base + llg_slot(3 + c, s), pd[c] + off);
+            if (HAS_O && fo) cp_async8(base + llg_slot(6 + c, s), po[c] + off);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ V6 get_m(int s) const {
+        V6 o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 f = lds64f(base + llg_slot(c, s));
+            o.v[c][0] = (double)f.x;
+            o.v[c][1] = (double)f.y;
+        }
+        return o;
+    }
+    __device__ __forceinline__ V6 get_f(int field0, int s, bool have) const {
+        V6 o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 f = have ? lds64f(base + llg_slot(field0 + c, s)) : make_float2(0.f, 0.f);
+            o.v[c][0] = (double)f.x;
+            o.v[c][1] = (double)f.y;
+        }
+        return o;
+    }
+    __device__ __forceinline__ V6 direct_m(int64_t off) const {
+        V6 o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 f = __ldg(reinterpret_cast<const float2*>(pm[c] + off));
+            o.v[c][0] = (double)f.x;
+            o.v[c][1] = (double)f.y;
+        }
+        return o;
+    }
+    // the three components' two mask bytes of one row, packed: bit 0 of byte (2 c + i) = pixel i of component c observed
+    __device__ __forceinline__ uint2 masks(int64_t off) const {
+        unsigned lo = 0u, hi = 0u;
+        if (HAS_O) {
+            const unsigned k0 = __ldg(reinterpret_cast<const unsigned short*>(pk[0] + off));
+            const unsigned k1 = __ldg(reinterpret_cast<const unsigned short*>(pk[1] + off));
+            const unsigned k2 = __ldg(reinterpret_cast<const unsigned short*>(pk[2] + off));
+            lo = k0 | (k1 << 16);
+            hi = k2;
+        }
+        return make_uint2(lo, hi);
+    }
+};
+
+__device__ __forceinline__ unsigned mask_bit(const uint2& k, int c, int i) {
+    const unsigned w = c < 2 ? k.x : k.y;
+    return w & (1u << (16 * (c & 1) + 8 * i));
+}
+
+// unscaled 5-point sums of one row for the lane's two columns of one component
+__device__ __forceinline__ void lap2(const double* up, const double* ct, const double* dn, double lf, double rt, double* s) {
+    s[0] = ((up[0] + dn[0]) + (lf + ct[1])) - 4.0 * ct[0];
+    s[1] = ((up[1] + dn[1]) + (ct[0] + rt)) - 4.0 * ct[1];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass 1: S_u, S_pde of one u work item.  Iteration `it` handles row j = ys + it with the window mu = m[j-1], mc = m[j],
+// md = m[j+1]; ring element s is row ys + s: md comes from element it+1, dmdt / obs from element it.
+// ---------------------------------------------------------------------------------------------------------
+template <bool HAS_D, bool HAS_O, bool LEAN>
+__device__ __forceinline__ void llg_march_reduce_item(const Params& p, const LlgMarchGeom& g, const LlgLane& m, unsigned char* ring_mem,
+                                                      double& s_u, double& s_p) {
+    LlgRing<HAS_D, HAS_O> ring;
+    ring.bind(p, m, ring_mem);
+    const int W = p.W, n_it = LEAN ? g.R : m.ye - m.ys;
+    LlgK k;
+    k.h[0] = __ldg(p.coef + 3 * m.b);
+    k.h[1] = __ldg(p.coef + 3 * m.b + 1);
+    k.h[2] = __ldg(p.coef + 3 * m.b + 2);
+    k.kex = p.c_ex * p.inv_dx2;
+    k.g1 = p.tau * p.gamma;
+    k.g2 = p.tau * p.alpha;
+    auto off_of = [&](int e) -> int64_t { return LEAN ? (int64_t)(m.ys + e) * W : (int64_t)row_offset(p, m.ys + e); };
+#pragma unroll
+    for (int s = 0; s < kLR; ++s) ring.issue(s, off_of(s), s >= 1 && s <= n_it, s < n_it, s < n_it);
+    V6 mu = ring.direct_m(off_of(-1)), mc = ring.direct_m(off_of(0));
+    uint2 mk = ring.masks(off_of(0));
+    double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
+
+    auto row = [&](int it, auto J, bool refill_m, bool refill_f) {
+        constexpr int j = decltype(J)::value;
+        cp_async_wait<kLR - 2>();                                     // elements <= it + 1 have landed
+        const V6 md = ring.get_m(j + 1);
+        const V6 dt = ring.get_f(3, j, HAS_D), ob = ring.get_f(6, j, HAS_O);
+        ring.issue(j, off_of(it + kLR), refill_m, refill_f, refill_f);
+        const uint2 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : make_uint2(0u, 0u);
+        double lap[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double lf = __shfl_up_sync(0xffffffffu, mc.v[c][1], 1), rt = __shfl_down_sync(0xffffffffu, mc.v[c][0], 1);
+            if (!LEAN) {
+                if (m.left_edge) lf = mc.v[c][1];                     // reflect: m[-1] = m[1]
+                if (m.right_edge) rt = mc.v[c][0];
+            }
+            lap2(mu.v[c], mc.v[c], md.v[c], lf, rt, lap[c]);
+        }
+        const bool ok = LEAN ? true : (m.out_ok && it < n_it);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double mm[3] = {mc.v[0][i], mc.v[1][i], mc.v[2][i]}, ll[3] = {lap[0][i], lap[1][i], lap[2][i]};
+            const double dd[3] = {dt.v[0][i], dt.v[1][i], dt.v[2][i]};
+            double H[3], a[3], r[3];
+            llg_fwd_px(p, k, mm, ll, dd, H, a, r);
+            double& acc = i ? sp1 : sp0;
+            if (LEAN) {
+                acc = fma(r[0], r[0], acc);
+                acc = fma(r[1], r[1], acc);
+                acc = fma(r[2], r[2], acc);
+            } else {
+                fma_where(acc, r[0], r[0], ok);
+                fma_where(acc, r[1], r[1], ok);
+                fma_where(acc, r[2], r[2], ok);
+            }
+            if (HAS_O) {
+                double& au = i ? su1 : su0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double d = mm[c] - ob.v[c][i];
+                    fma_where(au, d, d, ok ? mask_bit(mk, c, i) : 0u);
+                }
+            }
+        }
+        mu = mc;
+        mc = md;
+        mk = mk_next;
+    };
+
+    const int groups = (n_it + kLR - 1) / kLR;
+    if (LEAN) {                                                       // n_it = R is a multiple of the ring depth
+#pragma unroll 1
+        for (int gi = 0; gi < groups - 1; ++gi)
+            static_for<kLR>([&](auto J) { row(gi * kLR + decltype(J)::value, J, true, true); });
+        static_for<kLR>([&](auto J) { row((groups - 1) * kLR + decltype(J)::value, J, decltype(J)::value == 0, false); });
+    } else {
+#pragma unroll 1
+        for (int gi = 0; gi < groups; ++gi)
+            static_for<kLR>([&](auto J) {
+                const int it = gi * kLR + decltype(J)::value, sn = it + kLR;
+                row(it, J, sn <= n_it, sn < n_it);
+            });
+    }
+    cp_async_wait<0>();
+    if (m.out_ok) {
+        s_p += sp0 + sp1;
+        s_u += su0 + su1;
+    }
+}
+
+template <bool HAS_D, bool HAS_O, int PART>
+__global__ void __launch_bounds__(kLlgThreads, 3)
+llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, double* __restrict__ partials,
+                        unsigned int* __restrict__ ticket, double* __restrict__ sums, int finalize, double* __restrict__ scal,
+                        float* __restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char ring_mem[];
+    __shared__ double scratch[3 * (kLlgThreads / 32)];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
+    double s_a = 0.0, s_u = 0.0, s_p = 0.0;
+    if constexpr (PART == PART_LEAN) {
+        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
+            bool skip;
+            const LlgLane m = llg_lane_decode<true>(p, g, idx, lane, skip);
+            llg_march_reduce_item<HAS_D, HAS_O, true>(p, g, m, ring_mem, s_u, s_p);
+        }
+        block_sum3<kLlgThreads>(s_a, s_u, s_p, scratch);               // per-CTA partial -> slot; the REST kernel's last CTA adds them
+        if (tid == 0) {
+            partials[3 * blockIdx.x + 0] = 0.0;
+            partials[3 * blockIdx.x + 1] = s_u;
+            partials[3 * blockIdx.x + 2] = s_p;
+        }
+    } else {
+        auto do_a = [&](int item) { a_item_reduce(p, g.a, item, lane, s_a); };
+        auto do_u = [&](int item) {
+            bool skip;
+            const LlgLane m = llg_lane_decode<false>(p, g, item, lane, skip);
+            if (skip) return;                                          // the LEAN kernel's item (warp-uniform)
+            llg_march_reduce_item<HAS_D, HAS_O, false>(p, g, m, ring_mem, s_u, s_p);
+        };
+        run_interleaved(warp0, nwarps, g.n_items, p.has_a ? g.a.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+        reduce_epilogue_n<kLlgThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace, g.part_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass 2: seed gradient of one u work item.  Iteration `it` evaluates row j = ys - 1 + it (window mu = m[j-1], mc = m[j],
+// md = m[j+1]; residual, field gradient G_H[j], pointwise gradient L[j]) and then emits row jo = j - 1 from the G_H window
+// g2 = G_H[jo-1], g1 = G_H[jo], g0 = G_H[jo+1], the pointwise part kept from the previous iteration and the observation
+// term at m[jo] = mu.  Ring element s is row ys - 2 + s: md = element it+2, dmdt[j] = element it+1, obs[jo] = element it.
+// ---------------------------------------------------------------------------------------------------------
+template <bool HAS_D, bool HAS_O, bool LEAN>
+__device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMarchGeom& g, const LlgLane& m, unsigned char* ring_mem, double c_u,
+                                                   double c_p, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    LlgRing<HAS_D, HAS_O> ring;
+    ring.bind(p, m, ring_mem);
+    const int W = p.W, rows = LEAN ? g.R : m.ye - m.ys, n_it = rows + 2;
+    const int64_t plane = (int64_t)p.H * W;
+    LlgK k;
+    k.h[0] = __ldg(p.coef + 3 * m.b);
+    k.h[1] = __ldg(p.coef + 3 * m.b + 1);
+    k.h[2] = __ldg(p.coef + 3 * m.b + 2);
+    k.kex = p.c_ex * p.inv_dx2;
+    k.g1 = p.tau * p.gamma;
+    k.g2 = p.tau * p.alpha;
+    const double cl = -c_p * p.tau, ck = cl * k.kex;                  // d loss / d m = cl G_m + ck K^T G_H + observation term
+    float* gm = g_x0 + ((int64_t)m.b * p.C + p.ch_a) * plane + m.colc;
+    float* gd = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + p.ch_a) * plane + m.colc : nullptr;
+    auto off_of = [&](int e) -> int64_t { return LEAN ? (int64_t)(m.ys - 2 + e) * W : (int64_t)row_offset(p, m.ys - 2 + e); };
+    // fields of element s that are consumed: m for s in [2, n_it+2), dmdt for s in [1, n_it+1), obs for s in [2, n_it)
+#pragma unroll
+    for (int s = 0; s < kLR; ++s) ring.issue(s, off_of(s), s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
+    V6 mu = ring.direct_m(off_of(0)), mc = ring.direct_m(off_of(1));
+    V6 g2{}, g1{}, lp{};                                              // G_H[jo-1], G_H[jo], pointwise part of row jo
+    uint2 mk = make_uint2(0u, 0u);                                    // masks of the row emitted in THIS iteration
+    // column weights of the transposed stencil (general path): neighbour q counts twice when it lies on an edge column
+    const double wl0 = LEAN ? 1.0 : (m.left_edge ? 0.0 : (m.col0 - 1 == 0 ? 2.0 : 1.0));        // left neighbour of pixel 0 (other lane)
+    const double wl1 = LEAN ? 1.0 : (m.col0 == 0 ? 2.0 : 1.0);                                  // left neighbour of pixel 1 = pixel 0
+    const double wr0 = LEAN ? 1.0 : (m.col0 + 1 == p.W - 1 ? 2.0 : 1.0);                        // right neighbour of pixel 0 = pixel 1
+    const double wr1 = LEAN ? 1.0 : (m.right_edge ? 0.0 : (m.col0 + 2 == p.W - 1 ? 2.0 : 1.0)); // right neighbour of pixel 1 (other lane)
+
+    auto row = [&](int it, auto J, bool refill_m, bool refill_d, bool refill_o) {
+        constexpr int j = decltype(J)::value;
+        cp_async_wait<kLR - 3>();                                     // elements <= it + 2 have landed
+        const V6 md = ring.get_m(j + 2);
+        const V6 dt = ring.get_f(3, j + 1, HAS_D), ob = ring.get_f(6, j, HAS_O);
+        ring.issue(j, off_of(it + kLR), refill_m, refill_d, refill_o);
+        const int y = m.ys - 1 + it, jo = y - 1;                       // evaluated row, emitted row (local)
+        const uint2 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : make_uint2(0u, 0u);
+        // ---- forward + backward at row y
+        double lap[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double lf = __shfl_up_sync(0xffffffffu, mc.v[c][1], 1), rt = __shfl_down_sync(0xffffffffu, mc.v[c][0], 1);
+            if (!LEAN) {
+                if (m.left_edge) lf = mc.v[c][1];
+                if (m.right_edge) rt = mc.v[c][0];
+            }
+            lap2(mu.v[c], mc.v[c], md.v[c], lf, rt, lap[c]);
+        }
+        // the residual exists for rows ylo-1 .. yhi that lie inside the global grid; elsewhere G_H and L are zero
+        const bool need = LEAN ? true : (y >= p.ylo - 1 && y <= p.yhi && y + p.yg0 >= 0 && y + p.yg0 < p.Hg && m.lane_ok);
+        V6 g0, ln;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double mm[3] = {mc.v[0][i], mc.v[1][i], mc.v[2][i]}, ll[3] = {lap[0][i], lap[1][i], lap[2][i]};
+            const double dd[3] = {dt.v[0][i], dt.v[1][i], dt.v[2][i]};
+            double H[3], a[3], r[3], GH[3], Gm[3];
+            llg_fwd_px(p, k, mm, ll, dd, H, a, r);
+            llg_bwd_px(p, mm, H, a, r, GH, Gm);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                g0.v[c][i] = need ? GH[c] : 0.0;
+                ln.v[c][i] = need ? Gm[c] : 0.0;
+            }
+            if (gd && it >= 1 && y < m.ye && m.out_ok) {              // d loss / d dmdt = c_p r (row y is an owned row)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gd[c * plane + (int64_t)y * W + i] = (float)(c_p * r[c]);
+            }
+        }
+        // ---- emit row jo = y - 1
+        const bool emit = LEAN ? (it >= 2 && m.out_ok) : (it >= 2 && jo < m.ye && m.out_ok);
+        double wu = 1.0, wd = 1.0;
+        if (!LEAN) {                                                  // rows above / below: 2 from a boundary row, 0 from outside
+            const int gjo = jo + p.yg0;
+            wu = gjo == 0 ? 0.0 : (gjo == 1 ? 2.0 : 1.0);
+            wd = gjo == p.Hg - 1 ? 0.0 : (gjo == p.Hg - 2 ? 2.0 : 1.0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double l = __shfl_up_sync(0xffffffffu, g1.v[c][1], 1), q = __shfl_down_sync(0xffffffffu, g1.v[c][0], 1);
+            double a0, a1;
+            if (LEAN) {
+                a0 = ((g2.v[c][0] + g0.v[c][0]) + (l + g1.v[c][1])) - 4.0 * g1.v[c][0];
+                a1 = ((g2.v[c][1] + g0.v[c][1]) + (g1.v[c][0] + q)) - 4.0 * g1.v[c][1];
+            } else {
+                a0 = ((wu * g2.v[c][0] + wd * g0.v[c][0]) + (wl0 * l + wr0 * g1.v[c][1])) - 4.0 * g1.v[c][0];
+                a1 = ((wu * g2.v[c][1] + wd * g0.v[c][1]) + (wl1 * g1.v[c][0] + wr1 * q)) - 4.0 * g1.v[c][1];
+            }
+            double v0 = fma(ck, a0, cl * lp.v[c][0]), v1 = fma(ck, a1, cl * lp.v[c][1]);
+            if (HAS_O) {                                              // mu is m of the emitted row
+                fma_where(v0, c_u, mu.v[c][0] - ob.v[c][0], mask_bit(mk, c, 0));
+                fma_where(v1, c_u, mu.v[c][1] - ob.v[c][1], mask_bit(mk, c, 1));
+            }
+            if (emit) *reinterpret_cast<float2*>(gm + c * plane + (int64_t)jo * W) = make_float2((float)v0, (float)v1);
+        }
+        g2 = g1;
+        g1 = g0;
+        lp = ln;
+        mu = mc;
+        mc = md;
+        mk = mk_next;
+    };
+    // masks of the first emitted row (element 2) are fetched by iteration 1 (mk_next of it = 1 is row element 2)
+    const int groups = (n_it + kLR - 1) / kLR;
+    if (LEAN) {                                                       // n_it = R + 2 is a multiple of the ring depth, >= 2 groups
+#pragma unroll 1
+        for (int gi = 0; gi < groups - 1; ++gi)
+            static_for<kLR>([&](auto J) { row(gi * kLR + decltype(J)::value, J, true, true, true); });
+        static_for<kLR>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            row((groups - 1) * kLR + j, J, j <= 1, j == 0, false);    // elements n_it, n_it + 1 (m) and n_it (dmdt) only
+        });
+    } else {
+#pragma unroll 1
+        for (int gi = 0; gi < groups; ++gi)
+            static_for<kLR>([&](auto J) {
+                const int it = gi * kLR + decltype(J)::value, sn = it + kLR;
+                row(it, J, sn < n_it + 2, sn < n_it + 1, sn < n_it);
+            });
+    }
+    cp_async_wait<0>();
+}
+
+template <bool HAS_D, bool HAS_O, int PART>
+__global__ void __launch_bounds__(kLlgThreads, 3)
+llg_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, const double* __restrict__ scal,
+                     const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    extern __shared__ __align__(16) unsigned char ring_mem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
+    const double up = upstream ? __ldg(upstream) : 1.0;
+    const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
+    if constexpr (PART == PART_LEAN) {
+        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
+            bool skip;
+            const LlgLane m = llg_lane_decode<true>(p, g, idx, lane, skip);
+            llg_march_vjp_item<HAS_D, HAS_O, true>(p, g, m, ring_mem, c_u, c_p, g_x0, nullptr);
+        }
+    } else {
+        auto do_a = [&](int item) { a_item_vjp(p, g.a, item, lane, c_a, g_x0, g_dxdt); };
+        auto do_u = [&](int item) {
+            bool skip;
+            const LlgLane m = llg_lane_decode<false>(p, g, item, lane, skip);
+            if (skip) return;
+            llg_march_vjp_item<HAS_D, HAS_O, false>(p, g, m, ring_mem, c_u, c_p, g_x0, g_dxdt);
+        };
+        run_interleaved(warp0, nwarps, g.n_items, g.a.n_a_items, (tid >> 5) & 1, do_u, do_a);
+    }
+}
