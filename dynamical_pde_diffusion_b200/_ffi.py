@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libdpde_b200.so")
+LIB_PATH = os.environ.get("DPDE_B200_LIB") or os.path.join(_PKG, "lib", "libdpde_b200.so")   # the override is for kernel experiments
 
 F32, F64, U8 = 0, 1, 2
 PDE_NONE, PDE_HEAT, PDE_LLG_NORM, PDE_LLG_RESIDUAL = 0, 1, 2, 3

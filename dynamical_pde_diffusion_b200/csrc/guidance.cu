@@ -753,8 +753,9 @@ std::atomic<bool> g_fast_path{true};
 // sector aligned), 1 = 120 + 1 in both, 2 = 112 + 2 in both;
 // [1] unused; [2] rows per chunk (0 = automatic); [3] / [4] 1 = pair a-planes with u-planes in the
 // reduce / VJP pass (measured slower than separate streaming items on 8x2x4096^2: 3.0 vs 3.8 TB/s);
-// [5] 1 = interior work items take the general loops too (A/B runs of the lean interior loops);
-// [6] 1 = the LLG m x H_eff residual runs the round-1 tile kernels on every width (default: marching kernels for W >= 128)
+// [5] 1 = the LLG marching kernels send interior work items through their general loop too (A/B runs of the lean loop);
+// [6] 1 = the LLG m x H_eff residual runs the tile kernels on every size, 2 = the marching kernels on every size with W >= 128
+//     (default: marching on large grids, tiles on small ones)
 std::atomic<int> g_tuning[8] = {};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -788,8 +789,7 @@ inline int pairing(const Params& p, bool vjp) {
     return ((vjp ? g_tuning[4] != 0 : g_tuning[3] != 0) && p.ch_a >= 1 && p.ch_a == p.n_u_units) ? (p.has_a ? 1 : 2) : 0;
 }
 
-// `lean_ok`: may interior work items go to the LEAN kernel (no g_dxdt output in the VJP, a-planes not paired)?
-MarchGeom march_geometry(const Params& p, bool vjp, bool lean_ok = true) {
+MarchGeom march_geometry(const Params& p, bool vjp) {
     MarchGeom g{};
     const int rows = p.yhi - p.ylo;
     if (p.W <= 128) {
@@ -813,8 +813,6 @@ MarchGeom march_geometry(const Params& p, bool vjp, bool lean_ok = true) {
     int R = vjp ? 128 : 64;
     while (R > 32 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < 2 * want_warps) R >>= 1;
     while (R > 4 && ((rows + R - 1) / R) * per_row_items / g.segs_per_warp < want_warps) R >>= 1;
-    // the VJP's lean interior loop runs R + 2 row iterations in groups of its ring depth (8): 126, 62, 30, 14
-    if (vjp && R >= 16) R -= 2;
     if (g_tuning[2] > 0) R = g_tuning[2];
     g.R = R;
     g.chunks = (rows + R - 1) / R;
@@ -824,25 +822,6 @@ MarchGeom march_geometry(const Params& p, bool vjp, bool lean_ok = true) {
     g.a_block4 = stream_block4(g.a_plane4, (int64_t)(p.ch_a > 0 ? p.ch_a : 1) * p.B);
     g.a_blocks_per_plane = (g.a_plane4 + g.a_block4 - 1) / g.a_block4;
     g.n_a_items = g.a_blocks_per_plane * p.ch_a * p.B;
-    // ---- interior rectangle (heat_march.cuh, "Three kernels"): strips none of whose 32 lanes is an edge or idle lane,
-    //      full chunks whose rows + stencil margin need neither reflection nor clamping, row iterations in whole groups
-    g.n_int_items = 0;
-    const int n_it = vjp ? R + 2 : R, margin = vjp ? 2 : 1;
-    if (lean_ok && g_tuning[5] == 0 && g.segs_per_warp == 1 && pairing(p, vjp) == 0 && n_it % kLeanRing == 0 && n_it >= (vjp ? 2 : 1) * kLeanRing) {
-        int s_lo = -1, s_hi = -2, c_lo = -1, c_hi = -2;
-        for (int st = 0; st < g.strips; ++st) {
-            const int first = st * g.strip_w - 4 * g.halo_lane, last = first + 4 * 31;
-            if (first >= 4 && last + 4 < p.W) { if (s_lo < 0) s_lo = st; s_hi = st; }
-        }
-        for (int c = 0; c < g.chunks; ++c) {
-            const int ys = p.ylo + c * R;
-            if (ys + R <= p.yhi && rows_inside(p, ys - margin, ys + R + margin - 1)) { if (c_lo < 0) c_lo = c; c_hi = c; }
-        }
-        if (s_lo >= 0 && c_lo >= 0) {
-            g.s_lo = s_lo; g.s_hi = s_hi; g.c_lo = c_lo; g.c_hi = c_hi;
-            g.n_int_items = p.B * p.n_u_units * (s_hi - s_lo + 1) * (c_hi - c_lo + 1);
-        }
-    }
     return g;
 }
 
@@ -876,33 +855,15 @@ template <typename K>
 int march_grid(K kernel, const MarchGeom& g, int smem, bool paired) {
     const int occ = march_occupancy(kernel, smem);
     const int64_t need = ((int64_t)g.n_warp_items + (paired ? 0 : g.n_a_items) + kThreads / 32 - 1) / (kThreads / 32);
-    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials / 2);
+    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials);
 }
 
-template <typename K>
-int lean_grid(K kernel, const MarchGeom& g) {
-    const int occ = march_occupancy(kernel, lean_ring_bytes());
-    const int64_t need = ((int64_t)g.n_int_items + kThreads / 32 - 1) / (kThreads / 32);
-    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials / 2);
-}
-
-// One pass = the LEAN kernel over the interior rectangle (when there is one) + the REST kernel, or the single ALL kernel.
 template <bool HAS_D, bool HAS_O, int PA, bool PS>
-int launch_march_reduce_parts(const Params& p, MarchGeom g, double* partials, unsigned int* ticket, double* sums, int finalize,
-                              double* scal, float* trace, cudaStream_t s) {
+int launch_march_reduce_pa(const Params& p, const MarchGeom& g, double* partials, unsigned int* ticket, double* sums, int finalize,
+                           double* scal, float* trace, cudaStream_t s) {
     constexpr int smem = ring_bytes(PA, false);
-    if (PA == 0 && g.n_int_items > 0) {
-        auto lean = heat_march_reduce_kernel<HAS_D, HAS_O, 0, PS, PART_LEAN>;
-        const int grid_a = lean_grid(lean, g);
-        lean<<<grid_a, kThreads, lean_ring_bytes(), s>>>(p, g, partials, ticket, sums, 0, scal, trace);
-        g.part_base = grid_a;
-        auto rest = heat_march_reduce_kernel<HAS_D, HAS_O, 0, PS, PART_REST>;
-        rest<<<march_grid(rest, g, smem, false), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
-    } else {
-        g.n_int_items = 0;
-        auto k = heat_march_reduce_kernel<HAS_D, HAS_O, PA, PS, PART_ALL>;
-        k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
-    }
+    auto k = heat_march_reduce_kernel<HAS_D, HAS_O, PA, PS>;
+    k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
     return check_launch("dpde_guidance_reduce (march)");
 }
 
@@ -911,36 +872,28 @@ int launch_march_reduce(const Params& p, double* partials, unsigned int* ticket,
                         float* trace, cudaStream_t s) {
     const MarchGeom g = march_geometry(p, false);
     switch (pairing(p, false)) {
-        case 1: return launch_march_reduce_parts<HAS_D, HAS_O, 1, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
-        case 2: return launch_march_reduce_parts<HAS_D, HAS_O, 2, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
-        default: return launch_march_reduce_parts<HAS_D, HAS_O, 0, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        case 1: return launch_march_reduce_pa<HAS_D, HAS_O, 1, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        case 2: return launch_march_reduce_pa<HAS_D, HAS_O, 2, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
+        default: return launch_march_reduce_pa<HAS_D, HAS_O, 0, false>(p, g, partials, ticket, sums, finalize, scal, trace, s);
     }
 }
 
 template <bool HAS_D, bool HAS_O, int PA, bool PS>
-int launch_march_vjp_parts(const Params& p, MarchGeom g, const double* scal, const double* upstream, float* g_x0, float* g_dxdt,
-                           cudaStream_t s) {
+int launch_march_vjp_pa(const Params& p, const MarchGeom& g, const double* scal, const double* upstream, float* g_x0, float* g_dxdt,
+                        cudaStream_t s) {
     constexpr int smem = ring_bytes(PA, true);
-    if (PA == 0 && g.n_int_items > 0) {
-        auto lean = heat_march_vjp_kernel<HAS_D, HAS_O, 0, PS, PART_LEAN>;
-        lean<<<lean_grid(lean, g), kThreads, lean_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
-        auto rest = heat_march_vjp_kernel<HAS_D, HAS_O, 0, PS, PART_REST>;
-        rest<<<march_grid(rest, g, smem, false), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
-    } else {
-        g.n_int_items = 0;
-        auto k = heat_march_vjp_kernel<HAS_D, HAS_O, PA, PS, PART_ALL>;
-        k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
-    }
+    auto k = heat_march_vjp_kernel<HAS_D, HAS_O, PA, PS>;
+    k<<<march_grid(k, g, smem, PA != 0), kThreads, smem, s>>>(p, g, scal, upstream, g_x0, g_dxdt);
     return check_launch("dpde_guidance_vjp (march)");
 }
 
 template <bool HAS_D, bool HAS_O>
 int launch_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
-    const MarchGeom g = march_geometry(p, true, g_dxdt == nullptr);
+    const MarchGeom g = march_geometry(p, true);
     switch (pairing(p, true)) {
-        case 1: return launch_march_vjp_parts<HAS_D, HAS_O, 1, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
-        case 2: return launch_march_vjp_parts<HAS_D, HAS_O, 2, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
-        default: return launch_march_vjp_parts<HAS_D, HAS_O, 0, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        case 1: return launch_march_vjp_pa<HAS_D, HAS_O, 1, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        case 2: return launch_march_vjp_pa<HAS_D, HAS_O, 2, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
+        default: return launch_march_vjp_pa<HAS_D, HAS_O, 0, false>(p, g, scal, upstream, g_x0, g_dxdt, s);
     }
 }
 
@@ -1022,14 +975,19 @@ int launch_llg_tile_vjp(const Params& p, const LlgGeom& L, const double* scal, c
 }
 
 // ---- LLG m x H_eff residual, marching kernels (llg_march.cuh) ---------------------------------------------
-inline bool llg_march_wanted(const Params& p) { return p.kind == DPDE_PDE_LLG_RESIDUAL && p.W >= 128 && g_tuning[6] == 0; }
+// Large grids only: measured on 8 x 6 x 2048^2 the marching pair runs 0.41 / 0.86 ms against 0.52 / 0.94 ms of the tile kernels,
+// on config 3's shard (32 x 6 x 128^2, L2 resident) 26 / 39 us against 19 / 21 us -- the tiles keep the small problems.
+inline bool llg_march_wanted(const Params& p) {
+    if (p.kind != DPDE_PDE_LLG_RESIDUAL || p.W < 128 || g_tuning[6] == 1) return false;
+    return g_tuning[6] == 2 || (int64_t)p.B * (p.yhi - p.ylo) * p.W >= (4ll << 20);          // key 6 = 2: marching on every size (tests)
+}
 
 LlgMarchGeom llg_march_geometry(const Params& p, bool vjp, bool lean_ok) {
     LlgMarchGeom g{};
     const int rows = p.yhi - p.ylo;
     g.strips = (p.W + kLlgStrip - 1) / kLlgStrip;
     const int64_t per_row_items = (int64_t)g.strips * p.B;
-    // rows per chunk: long chunks amortise the warm-up rows, short ones give every resident warp (12 per SM) a few items
+    // rows per chunk: long chunks amortise the warm-up rows, short ones give every resident warp a few items
     const int64_t want_warps = (int64_t)sm_count() * 12;
     int R = 64;
     while (R > 8 && ((rows + R - 1) / R) * per_row_items < 2 * want_warps) R >>= 1;
@@ -1042,8 +1000,8 @@ LlgMarchGeom llg_march_geometry(const Params& p, bool vjp, bool lean_ok) {
     g.a.a_block4 = stream_block4(g.a.a_plane4, p.B);
     g.a.a_blocks_per_plane = (g.a.a_plane4 + g.a.a_block4 - 1) / g.a.a_block4;
     g.a.n_a_items = g.a.a_blocks_per_plane * p.ch_a * p.B;
-    // interior rectangle: strips whose 32 lanes all hold grid columns away from the edge columns, full chunks whose rows +
-    // stencil margin need neither reflection nor clamping, row iterations in whole groups of the ring depth
+    // interior rectangle (lean loop): strips whose 32 lanes all hold grid columns away from the edge columns, full chunks whose
+    // rows + stencil margin need neither reflection nor clamping, row iterations in whole groups of the ring depth
     const int n_it = vjp ? R + 2 : R, margin = vjp ? 2 : 1;
     if (lean_ok && g_tuning[5] == 0 && n_it % kLR == 0 && n_it >= (vjp ? 2 : 1) * kLR) {
         int s_lo = -1, s_hi = -2, c_lo = -1, c_hi = -2;
@@ -1068,34 +1026,23 @@ int llg_march_grid(K kernel, int64_t warp_items) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLlgThreads, llg_ring_bytes()) != cudaSuccess || occ < 1) occ = 1;
     const int64_t need = (warp_items + kLlgThreads / 32 - 1) / (kLlgThreads / 32);
-    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials / 2);
+    return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials);
 }
 
 template <bool HAS_D, bool HAS_O>
 int launch_llg_march_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal, float* trace,
                             cudaStream_t s) {
-    LlgMarchGeom g = llg_march_geometry(p, false, true);
-    if (g.n_int_items > 0) {
-        auto lean = llg_march_reduce_kernel<HAS_D, HAS_O, PART_LEAN>;
-        const int grid_a = llg_march_grid(lean, g.n_int_items);
-        lean<<<grid_a, kLlgThreads, llg_ring_bytes(), s>>>(p, g, partials, ticket, sums, 0, scal, trace);
-        g.part_base = grid_a;
-    }
-    auto rest = llg_march_reduce_kernel<HAS_D, HAS_O, PART_REST>;
-    rest<<<llg_march_grid(rest, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, partials, ticket, sums, finalize,
-                                                                                                       scal, trace);
+    const LlgMarchGeom g = llg_march_geometry(p, false, true);
+    auto k = llg_march_reduce_kernel<HAS_D, HAS_O>;
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
     return check_launch("dpde_guidance_reduce (llg march)");
 }
 
 template <bool HAS_D, bool HAS_O>
 int launch_llg_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, true, g_dxdt == nullptr);
-    if (g.n_int_items > 0) {
-        auto lean = llg_march_vjp_kernel<HAS_D, HAS_O, PART_LEAN>;
-        lean<<<llg_march_grid(lean, g.n_int_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
-    }
-    auto rest = llg_march_vjp_kernel<HAS_D, HAS_O, PART_REST>;
-    rest<<<llg_march_grid(rest, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    auto k = llg_march_vjp_kernel<HAS_D, HAS_O>;
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
     return check_launch("dpde_guidance_vjp (llg march)");
 }
 
@@ -1164,15 +1111,15 @@ inline int64_t per_sample_item_bound(int B, int Cu, int H, int W) {
 template <bool HAS_D>
 int launch_march_per_sample_reduce(const Params& p, double* partials, double* out, cudaStream_t s) {
     const MarchGeom g = march_geometry(p, false);
-    if (int rc = launch_march_reduce_parts<HAS_D, false, 0, true>(p, g, partials, nullptr, nullptr, 0, nullptr, nullptr, s)) return rc;
+    if (int rc = launch_march_reduce_pa<HAS_D, false, 0, true>(p, g, partials, nullptr, nullptr, 0, nullptr, nullptr, s)) return rc;
     per_sample_items_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(partials, g.n_seg_items / p.B, p.B, out);
     return check_launch("dpde_heat_residual_sq (march)");
 }
 
 template <bool HAS_D>
 int launch_march_per_sample_vjp(const Params& p, const double* upstream, float* g_u, float* g_dudt, cudaStream_t s) {
-    const MarchGeom g = march_geometry(p, true, g_dudt == nullptr);
-    return launch_march_vjp_parts<HAS_D, false, 0, true>(p, g, nullptr, upstream, g_u, g_dudt, s);
+    const MarchGeom g = march_geometry(p, true);
+    return launch_march_vjp_pa<HAS_D, false, 0, true>(p, g, nullptr, upstream, g_u, g_dudt, s);
 }
 
 View to_view(const dpde_view& v) { return View{v.ptr, v.dtype, v.stride_b, v.stride_c}; }

@@ -33,14 +33,7 @@ struct MarchGeom {
     int a_blocks_per_plane, n_a_items;   // a-plane work: blocks of kABlock float4 within one plane's owned rows
     int a_plane4;                        // float4 per a-plane (owned rows)
     int a_block4;                        // float4 per a-plane work item (kABlock, smaller on small problems)
-    // interior rectangle of u work items (strips s_lo..s_hi x chunks c_lo..c_hi, empty when n_int_items == 0): full chunks
-    // whose rows (+ the stencil margin) lie inside grid and buffer, strips without an edge column.  They run in their own
-    // LEAN kernel; everything else (and the a-planes) in the REST kernel -- see "Three kernels" below.
-    int s_lo, s_hi, c_lo, c_hi, n_int_items;
-    int part_base;                       // REST kernel: first per-CTA partial slot it owns (= grid of the LEAN kernel)
 };
-
-enum { PART_ALL = 0, PART_LEAN = 1, PART_REST = 2 };
 
 constexpr int kABlock = 1024;            // largest a-plane work item, in float4 (4096 pixels)
 
@@ -53,8 +46,6 @@ __device__ __forceinline__ uchar4 ldg4(const unsigned char* p) { return __ldg(re
 // (PA == 1; PA == 2: mask_a empty, nothing to read, ring as PA = 0) ride in the same ring element -- 4 deep, 90112 B.
 // The reduce pass carries no residual window and no output pointers: it fits 80 registers, so with a 4-deep ring
 // (53 KB) THREE CTAs share an SM (24 warps instead of 16) -- it is issue-bound, not bandwidth-bound.
-constexpr int kLeanRing = 8;             // rows per lane in flight in the LEAN kernels
-__host__ __device__ constexpr int lean_ring_bytes() { return kLeanRing * kThreads * (3 * 16 + 4); }
 __host__ __device__ constexpr int ring_depth(int PA, bool vjp) { return (PA == 1 || !vjp) ? 4 : 8; }
 __host__ __device__ constexpr int ring_bytes(int PA, bool vjp) { return ring_depth(PA, vjp) * kThreads * (PA == 1 ? 5 * 16 + 2 * 4 : 3 * 16 + 4); }
 
@@ -83,52 +74,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // exact uint8 -> double without the (quarter-rate) I2F.F64: 2^52 + k has k in its low mantissa bits
 __device__ __forceinline__ double u8_to_double(unsigned k) { return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0; }
 
-
-// ---------------------------------------------------------------------------------------------------------
-// Lean loops for INTERIOR work items (round 2).  ncu of the round-1 kernels: 145 instructions per row iteration in the
-// reduce pass of which only 44 were fp64 arithmetic and 12 conversions -- the rest was address arithmetic (four 64-bit
-// addresses rebuilt from constant-bank pointers per row), dynamic ring-slot indexing, the reflect / clamp row loader,
-// edge selects, mask widening (uint8 -> fp64 + multiply) and per-row validity flags; issue slots, not DRAM, were the
-// limit (65 % issue-active at 0.72 of the HBM peak).  An item is INTERIOR when every row it touches lies inside the
-// grid and the buffer, it is a full chunk, and no lane of the warp sits on a grid edge column -- all but the first /
-// last chunk of a plane and the two edge strips.  For those:
-//   * ring slots are compile-time (the loop is unrolled by exactly the ring depth), so every LDS / LDGSTS shared
-//     address is base + immediate;
-//   * four running 64-bit row pointers advance once per group of RD rows; the copy addresses inside a group are
-//     pointer + j * W (one IMAD.WIDE each);
-//   * no reflection, no clamps, no edge selects, no per-row validity: halo lanes accumulate into item-local sums that
-//     are dropped at the end of the item;
-//   * masks are 0 / 1 (the C ABI's DPDE_U8 operands are bool masks): the observation term is a predicated DFMA
-//     instead of widen + multiply + square.
-// Everything else (first / last chunks, edge strips, narrow grids, per-sample mode with g_dxdt, paired a-planes) runs
-// the general loops below, unchanged.
-// ---------------------------------------------------------------------------------------------------------
-template <int J>
-using IC = std::integral_constant<int, J>;
-
-template <int N, typename F>
-__device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (N > 0) {
-        static_for<N - 1>(f);
-        f(IC<N - 1>{});
-    }
-}
-
-// acc = fma(a, b, acc) where byte I of the mask word k is set (mask bytes are 0 / 1): a test + a PREDICATED DFMA -- the
-// C++ form `if (bit) acc = fma(...)` compiles to an unconditional DFMA and two FSELs
-template <int I>
-__device__ __forceinline__ void fma_if(double& acc, double a, double b, unsigned k) {
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 p, t, 0;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}"
-        : "+d"(acc) : "d"(a), "d"(b), "r"(k), "n"(1u << (8 * I)));
-}
-
 struct D4v {
     double v[4];
 };
 __device__ __forceinline__ D4v widen(const float4& f) { return D4v{{(double)f.x, (double)f.y, (double)f.z, (double)f.w}}; }
 
 struct MarchLane {
-    int b, cu, col0, ys, ye, strip, chunk;
+    int b, cu, col0, ys, ye;
     bool lane_ok, out_ok, left_edge, right_edge;
 };
 
@@ -151,8 +103,6 @@ __device__ __forceinline__ MarchLane march_decode(const Params& p, const MarchGe
     m.right_edge = (m.col0 + 4 == p.W);
     m.ys = p.ylo + (int)chunk * g.R;
     m.ye = min(m.ys + g.R, p.yhi);
-    m.strip = strip;
-    m.chunk = (int)chunk;
     return m;
 }
 
@@ -270,6 +220,23 @@ __device__ __forceinline__ AItem a_decode(const Params& p, const MarchGeom& g, i
     return a;
 }
 
+template <int J>
+using IC = std::integral_constant<int, J>;
+
+// compile-time loop: f(IC<0>{}), ..., f(IC<N-1>{})
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(IC<N - 1>{});
+    }
+}
+
+// Is every row of [first, last] inside the local buffer and inside the global grid (no reflection, no clamp)?
+__host__ __device__ __forceinline__ bool rows_inside(const Params& p, int first, int last) {
+    return first >= 0 && last <= p.H - 1 && first + p.yg0 >= 0 && last + p.yg0 <= p.Hg - 1;
+}
+
 // ---- a-plane streaming items (sum (mask (a - obs))^2 and its gradient), shared by the heat and LLG kernels ---------
 // Masks are 0 / 1, so an unobserved pixel is handled by selecting the OBSERVATION operand at 32 bits before it is
 // widened: o' = mask ? obs : a makes the difference exactly zero -- one FSEL instead of widening the mask to fp64 and
@@ -286,8 +253,8 @@ __device__ __forceinline__ void a_item_reduce(const Params& p, const MarchGeom& 
     auto body = [&](int i) {
         const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
         const unsigned k = __ldg(reinterpret_cast<const unsigned*>(pm + 4 * i));
-        const double d0 = (double)v.x - (double)sel_obs(k & 0xffu, o.x, v.x), d1 = (double)v.y - (double)sel_obs(k & 0xff00u, o.y, v.y);
-        const double d2 = (double)v.z - (double)sel_obs(k & 0xff0000u, o.z, v.z), d3 = (double)v.w - (double)sel_obs(k & 0xff000000u, o.w, v.w);
+        const double d0 = (double)v.x - (double)(sel_obs(k & 0xffu, o.x, v.x)), d1 = (double)v.y - (double)(sel_obs(k & 0xff00u, o.y, v.y));
+        const double d2 = (double)v.z - (double)(sel_obs(k & 0xff0000u, o.z, v.z)), d3 = (double)v.w - (double)(sel_obs(k & 0xff000000u, o.w, v.w));
         s0 = fma(d0, d0, s0);
         s1 = fma(d1, d1, s1);
         s0 = fma(d2, d2, s0);
@@ -317,10 +284,10 @@ __device__ __forceinline__ void a_item_vjp(const Params& p, const MarchGeom& g, 
             const float4 v = ldg4(pa + 4 * i), o = ldg4(po + 4 * i);
             const unsigned k = __ldg(reinterpret_cast<const unsigned*>(pm + 4 * i));
             float4 w;
-            w.x = (float)(c_a * ((double)v.x - (double)sel_obs(k & 0xffu, o.x, v.x)));
-            w.y = (float)(c_a * ((double)v.y - (double)sel_obs(k & 0xff00u, o.y, v.y)));
-            w.z = (float)(c_a * ((double)v.z - (double)sel_obs(k & 0xff0000u, o.z, v.z)));
-            w.w = (float)(c_a * ((double)v.w - (double)sel_obs(k & 0xff000000u, o.w, v.w)));
+            w.x = (float)(c_a * ((double)v.x - (double)(sel_obs(k & 0xffu, o.x, v.x))));
+            w.y = (float)(c_a * ((double)v.y - (double)(sel_obs(k & 0xff00u, o.y, v.y))));
+            w.z = (float)(c_a * ((double)v.z - (double)(sel_obs(k & 0xff0000u, o.z, v.z))));
+            w.w = (float)(c_a * ((double)v.w - (double)(sel_obs(k & 0xff000000u, o.w, v.w))));
             *reinterpret_cast<float4*>(pg + 4 * i) = w;
         };
         int i0 = 0;
@@ -358,57 +325,13 @@ __device__ __forceinline__ void run_interleaved(int warp0, int nwarps, int n_u, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Three kernels per pass (round 2).  The lean interior loop and the general loop must not share a kernel: inlined side by
-// side they spilled inside both loops (80-register reduce kernel: 0.394 ms instead of 0.336 ms), and as __noinline__
-// functions the general loop and the a-plane streaming read the parameter block through a generic pointer -- ncu showed
-// integer instructions waiting on the long scoreboard for p.* loads (VJP: 1.13 ms).  So the host launches
-//   PART_LEAN  the interior rectangle of u work items, lean loop only (no a-planes, no epilogue: per-CTA partial -> slot),
-//   PART_REST  the remaining u items with the general loop + all a-plane items + the reduction epilogue over BOTH
-//              kernels' partial slots (stream order makes the LEAN kernel's slots final),
-// or, when the rectangle is empty (narrow or small grids, tuning key 5), the single PART_ALL kernel of round 1.
-// ---------------------------------------------------------------------------------------------------------
-struct Sums3 {
-    double a, u, p;
-};
-
-// Is every row of [first, last] inside the local buffer and inside the global grid (no reflection, no clamp)?
-__host__ __device__ __forceinline__ bool rows_inside(const Params& p, int first, int last) {
-    return first >= 0 && last <= p.H - 1 && first + p.yg0 >= 0 && last + p.yg0 <= p.Hg - 1;
-}
-
-__device__ __forceinline__ bool in_interior(const MarchGeom& g, int strip, int chunk) {
-    return g.n_int_items > 0 && strip >= g.s_lo && strip <= g.s_hi && chunk >= g.c_lo && chunk <= g.c_hi;
-}
-
-// LEAN kernel: interior item index -> lane geometry (all 32 lanes valid output-or-halo lanes of one strip)
-struct LeanItem {
-    int b, cu, col0, ys, si;             // si: index of the item in the general (b, unit, strip, chunk) ordering
-    bool out_ok;
-};
-__device__ __forceinline__ LeanItem lean_decode(const Params& p, const MarchGeom& g, int idx, int lane) {
-    LeanItem m;
-    unsigned t = (unsigned)idx / (unsigned)p.B;
-    m.b = (int)((unsigned)idx - t * p.B);
-    unsigned t2 = t / (unsigned)p.n_u_units;
-    m.cu = (int)(t - t2 * p.n_u_units);
-    const unsigned ns = (unsigned)(g.s_hi - g.s_lo + 1);
-    const unsigned cc = t2 / ns;
-    const int strip = g.s_lo + (int)(t2 - cc * ns), chunk = g.c_lo + (int)cc;
-    m.col0 = strip * g.strip_w - 4 * g.halo_lane + 4 * lane;
-    m.out_ok = m.col0 >= strip * g.strip_w && m.col0 < (strip + 1) * g.strip_w;
-    m.ys = p.ylo + chunk * g.R;
-    m.si = m.b + p.B * (m.cu + p.n_u_units * (strip + g.strips * chunk));
-    return m;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // pass 1 (fast): S_a, S_u, S_pde
 // ---------------------------------------------------------------------------------------------------------
 // PS (per-sample mode, training loss models/loss.py:143): no global sums -- every row-segment item writes its own
 // sum of squared residuals to partials[item] (items of sample b are b, b + B, b + 2 B, ...: per_sample_items_kernel adds
 // them in that order), nothing else is touched.
-template <bool HAS_D, bool HAS_O, int PA, bool PS = false, int PART = PART_ALL>
-__global__ void __launch_bounds__(kThreads, PART == PART_LEAN ? 2 : 3)
+template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
+__global__ void __launch_bounds__(kThreads, 3)
 heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g,
                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
                          int finalize, double* __restrict__ scal, float* __restrict__ trace) {
@@ -416,114 +339,10 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     __shared__ double scratch[3 * (kThreads / 32)];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31;
-    double s_a = 0.0, s_u = 0.0, s_p = 0.0;
-    const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
-
-    if constexpr (PART == PART_LEAN) {
-        // ---- interior items only: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1];
-        //      ring element s is row ys + s: uc comes from element it+1, dudt / obs / mask from element it.
-        constexpr int RD = kLeanRing;                                  // 8 rows per lane in flight (the lean loop retires a row
-        constexpr unsigned F16 = RD * kThreads * 16;                   // in ~90 instructions: 2 rows of lead exposed the HBM latency)
-        const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;
-        const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
-        auto slot16 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); };
-        auto slot4 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); };
-        const int W = p.W, n_it = g.R;
-        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
-            const LeanItem m = lean_decode(p, g, idx, lane);
-            const int ch = p.ch_a + m.cu;
-            const int64_t first = (int64_t)m.ys * W + m.col0;          // running row pointers (lane's column included)
-            const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + first;
-            const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + first : nullptr;
-            const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + first : nullptr;
-            const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + first : nullptr;
-            const double a_s = __ldg(p.coef + m.b) * p.inv_dx2;
-            D4v ua = widen(ldg4(pu - W)), ub = widen(ldg4(pu));
-            static_for<RD>([&](auto J) {                               // prologue: elements 0 .. RD-1 (u of element 0 is ub)
-                constexpr int j = decltype(J)::value;
-                if (j >= 1) cp_async16(su + slot16(j), pu + j * W);
-                if (HAS_D) cp_async16(sd + slot16(j), pd + j * W);
-                if (HAS_O) {
-                    cp_async16(so + slot16(j), po + j * W);
-                    cp_async4(sm + slot4(j), pm + j * W);
-                }
-                cp_async_commit();
-            });
-            double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
-            auto group = [&](auto TAIL) {                              // RD row iterations; refills elements e0 + RD + j
-                constexpr bool tail = decltype(TAIL)::value;
-                pu += RD * W;
-                if (HAS_D) pd += RD * W;
-                if (HAS_O) { po += RD * W; pm += RD * W; }
-                static_for<RD>([&](auto J) {
-                    constexpr int j = decltype(J)::value;
-                    cp_async_wait<RD - 2>();                           // elements <= it + 1 have landed
-                    const D4v uc = widen(lds128(su + slot16(j + 1)));
-                    const float4 dt = HAS_D ? lds128(sd + slot16(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    unsigned k = 0u;
-                    if (HAS_O) {
-                        o = lds128(so + slot16(j));
-                        k = lds32(sm + slot4(j));
-                    }
-                    if (!tail) {                                       // element it + RD -> the slot just drained
-                        cp_async16(su + slot16(j), pu + j * W);
-                        if (HAS_D) cp_async16(sd + slot16(j), pd + j * W);
-                        if (HAS_O) {
-                            cp_async16(so + slot16(j), po + j * W);
-                            cp_async4(sm + slot4(j), pm + j * W);
-                        }
-                    } else if (j == 0) {                               // last group: only u of element n_it is still needed
-                        cp_async16(su + slot16(j), pu + j * W);
-                    }
-                    cp_async_commit();
-                    const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
-                    double sv[4];
-                    lap_row(ua, ub, uc, lf, rt, sv);
-                    const double r0 = (double)dt.x - a_s * sv[0], r1 = (double)dt.y - a_s * sv[1];
-                    const double r2 = (double)dt.z - a_s * sv[2], r3 = (double)dt.w - a_s * sv[3];
-                    sp0 = fma(r0, r0, sp0);
-                    sp1 = fma(r1, r1, sp1);
-                    sp0 = fma(r2, r2, sp0);
-                    sp1 = fma(r3, r3, sp1);
-                    if (HAS_O) {                                       // mask in {0, 1}: (mask (u - obs))^2 = mask ? (u - obs)^2 : 0
-                        const double d0 = ub.v[0] - (double)o.x, d1 = ub.v[1] - (double)o.y;
-                        const double d2 = ub.v[2] - (double)o.z, d3 = ub.v[3] - (double)o.w;
-                        fma_if<0>(su0, d0, d0, k);
-                        fma_if<1>(su1, d1, d1, k);
-                        fma_if<2>(su0, d2, d2, k);
-                        fma_if<3>(su1, d3, d3, k);
-                    }
-                    ua = ub;
-                    ub = uc;
-                });
-            };
-            const int groups = n_it / RD;
-#pragma unroll 1
-            for (int gi = 0; gi < groups - 1; ++gi) group(std::false_type{});
-            group(std::true_type{});
-            cp_async_wait<0>();
-            const double item_p = m.out_ok ? sp0 + sp1 : 0.0;          // halo lanes computed on neighbouring columns: dropped here
-            if (m.out_ok) s_u += su0 + su1;
-            if (PS) {
-                double v = item_p;
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) partials[m.si] = v;
-            } else {
-                s_p += item_p;
-            }
-        }
-        if (PS) return;
-        block_sum3(s_a, s_u, s_p, scratch);                            // per-CTA partial -> slot; the REST kernel's last CTA adds them
-        if (tid == 0) {
-            partials[3 * blockIdx.x + 0] = 0.0;
-            partials[3 * blockIdx.x + 1] = s_u;
-            partials[3 * blockIdx.x + 2] = s_p;
-        }
-        return;
-    } else {
     const float* x0 = reinterpret_cast<const float*>(p.x0.p);
     const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
+    double s_a = 0.0, s_u = 0.0, s_p = 0.0;
+    const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
 
     // ---- a-planes: sum (mask (a - obs))^2; a warp streams one block of a plane with 128-bit loads
     auto do_a = [&](int item) { a_item_reduce(p, g, item, lane, s_a); };
@@ -536,7 +355,6 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     ring.init(ring_mem, tid);
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
-        if (PART == PART_REST && in_interior(g, m.strip, m.chunk)) return;   // the LEAN kernel's item (warp-uniform: one segment per warp)
         ring.bind(p, m, x0, dxp);
         const int n_it = g.R, n_el = g.R + 1;
         ring.begin_item(p, m.ys, n_el - 1);
@@ -596,9 +414,7 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     run_interleaved(warp0, nwarps, g.n_warp_items, (PA == 0 && p.has_a) ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
     if (PS) return;
 
-    // this kernel's slots start at part_base (0 unless a LEAN kernel ran first); the last CTA adds ALL slots in index order
-    reduce_epilogue_n<kThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace, g.part_base);
-    }
+    reduce_epilogue(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -606,7 +422,7 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // PS (per-sample mode): `upstream` holds one seed per sample, c_p of an item = 2 upstream[b] (d r^2 / d r), no
 // observation terms, `scal` is not read.
-template <bool HAS_D, bool HAS_O, int PA, bool PS = false, int PART = PART_ALL>
+template <bool HAS_D, bool HAS_O, int PA, bool PS = false>
 __global__ void __launch_bounds__(kThreads, 2)
 heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, const double* __restrict__ scal,
                       const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
@@ -615,114 +431,10 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     const double up = (!PS && upstream) ? __ldg(upstream) : 1.0;
     const double c_a = PS ? 0.0 : __ldg(scal + 4) * up, c_u = PS ? 0.0 : __ldg(scal + 5) * up;
     double c_p = PS ? 0.0 : __ldg(scal + 6) * up;
-    const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
-
-    if constexpr (PART == PART_LEAN) {
-        // ---- interior items only.  Iteration `it` computes the residual of row j = ys - 1 + it (window ua = u[j-1], ub = u[j],
-        //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].
-        //      Ring element s is row ys - 2 + s:  uc = element it+2, dudt[j] = element it+1, obs/mask[jo] = element it.
-        constexpr int RD = kLeanRing;
-        constexpr unsigned F16 = RD * kThreads * 16;
-        const unsigned su = (unsigned)__cvta_generic_to_shared(ring_mem) + tid * 16, sd = su + F16, so = sd + F16;
-        const unsigned sm = (unsigned)__cvta_generic_to_shared(ring_mem) + 3 * F16 + tid * 4;
-        auto slot16 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 16); };
-        auto slot4 = [](int s) { return (unsigned)(s & (RD - 1)) * (kThreads * 4); };
-        const int W = p.W, n_it = g.R + 2;
-        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
-            const LeanItem m = lean_decode(p, g, idx, lane);
-            const int ch = p.ch_a + m.cu;
-            if (PS) c_p = 2.0 * __ldg(upstream + m.b);
-            const int64_t first = (int64_t)(m.ys - 2) * W + m.col0;    // ring element 0 = row ys - 2 (lane's column included)
-            const float* pu = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)ch * p.x0.sc + first;
-            const float* pd = HAS_D ? reinterpret_cast<const float*>(p.dxdt.p) + (int64_t)m.b * p.dxdt.sb + (int64_t)ch * p.dxdt.sc + first : nullptr;
-            const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)m.b * p.obs_u.sb + (int64_t)m.cu * p.obs_u.sc + first : nullptr;
-            const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + (int64_t)m.cu * p.mask_u.sc + first : nullptr;
-            float* pg = g_x0 + ((int64_t)m.b * p.C + ch) * ((int64_t)p.H * W) + first;   // output row of iteration `it` is element it
-            const double a_s = __ldg(p.coef + m.b) * p.inv_dx2, kp = -c_p * a_s;
-            D4v ua = widen(ldg4(pu)), ub = widen(ldg4(pu + W));
-            static_for<RD>([&](auto J) {                               // prologue: u / obs of elements >= 2, dudt of elements >= 1
-                constexpr int j = decltype(J)::value;
-                if (j >= 2) cp_async16(su + slot16(j), pu + j * W);
-                if (HAS_D && j >= 1) cp_async16(sd + slot16(j), pd + j * W);
-                if (HAS_O && j >= 2) {
-                    cp_async16(so + slot16(j), po + j * W);
-                    cp_async4(sm + slot4(j), pm + j * W);
-                }
-                cp_async_commit();
-            });
-            double r2[4] = {0.0, 0.0, 0.0, 0.0}, r1[4] = {0.0, 0.0, 0.0, 0.0};
-            auto group = [&](auto TAIL, bool first_group) {
-                constexpr bool tail = decltype(TAIL)::value;
-                pu += RD * W;
-                if (HAS_D) pd += RD * W;
-                if (HAS_O) { po += RD * W; pm += RD * W; }
-                static_for<RD>([&](auto J) {
-                    constexpr int j = decltype(J)::value;
-                    cp_async_wait<RD - 3>();                           // elements <= it + 2 have landed
-                    const D4v uc = widen(lds128(su + slot16(j + 2)));
-                    const float4 dt = HAS_D ? lds128(sd + slot16(j + 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    unsigned k = 0u;
-                    if (HAS_O) {
-                        o = lds128(so + slot16(j));
-                        k = lds32(sm + slot4(j));
-                    }
-                    if (!tail) {                                       // element it + RD -> the slot just drained
-                        cp_async16(su + slot16(j), pu + j * W);
-                        if (HAS_D) cp_async16(sd + slot16(j), pd + j * W);
-                        if (HAS_O) {
-                            cp_async16(so + slot16(j), po + j * W);
-                            cp_async4(sm + slot4(j), pm + j * W);
-                        }
-                    } else {                                           // last group: u of elements n_it, n_it + 1; dudt of element n_it
-                        if (j <= 1) cp_async16(su + slot16(j), pu + j * W);
-                        if (HAS_D && j == 0) cp_async16(sd + slot16(j), pd + j * W);
-                    }
-                    cp_async_commit();
-                    const double lf = __shfl_up_sync(0xffffffffu, ub.v[3], 1), rt = __shfl_down_sync(0xffffffffu, ub.v[0], 1);
-                    double sv[4], r0[4];
-                    lap_row(ua, ub, uc, lf, rt, sv);
-                    r0[0] = (double)dt.x - a_s * sv[0];
-                    r0[1] = (double)dt.y - a_s * sv[1];
-                    r0[2] = (double)dt.z - a_s * sv[2];
-                    r0[3] = (double)dt.w - a_s * sv[3];
-                    const double l1 = __shfl_up_sync(0xffffffffu, r1[3], 1), q1 = __shfl_down_sync(0xffffffffu, r1[0], 1);
-                    if ((j >= 2 || !first_group) && m.out_ok) {        // rows ys - 2, ys - 1 belong to the previous chunk
-                        // K^T r on an interior row / column: all weights are 1
-                        double v0 = kp * (((r2[0] + r0[0]) + (l1 + r1[1])) - 4.0 * r1[0]);
-                        double v1 = kp * (((r2[1] + r0[1]) + (r1[0] + r1[2])) - 4.0 * r1[1]);
-                        double v2 = kp * (((r2[2] + r0[2]) + (r1[1] + r1[3])) - 4.0 * r1[2]);
-                        double v3 = kp * (((r2[3] + r0[3]) + (r1[2] + q1)) - 4.0 * r1[3]);
-                        if (HAS_O) {                                   // mask in {0, 1}: c_u mask^2 (u - obs); ua is u of the output row
-                            fma_if<0>(v0, c_u, ua.v[0] - (double)o.x, k);
-                            fma_if<1>(v1, c_u, ua.v[1] - (double)o.y, k);
-                            fma_if<2>(v2, c_u, ua.v[2] - (double)o.z, k);
-                            fma_if<3>(v3, c_u, ua.v[3] - (double)o.w, k);
-                        }
-                        *reinterpret_cast<float4*>(pg + j * W) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        r2[i] = r1[i];
-                        r1[i] = r0[i];
-                    }
-                    ua = ub;
-                    ub = uc;
-                });
-                pg += RD * W;
-            };
-            const int groups = n_it / RD;
-            group(std::false_type{}, true);
-#pragma unroll 1
-            for (int gi = 1; gi < groups - 1; ++gi) group(std::false_type{}, false);
-            group(std::true_type{}, false);
-            cp_async_wait<0>();
-        }
-        return;
-    } else {
     const float* x0 = reinterpret_cast<const float*>(p.x0.p);
     const float* dxp = reinterpret_cast<const float*>(p.dxdt.p);
     const int64_t plane = (int64_t)p.H * p.W;
+    const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
 
     // ---- a-planes: g = c_a mask (mask (a - obs)), zeros when the mask is empty (sample.py:337-342)
     auto do_a = [&](int item) { a_item_vjp(p, g, item, lane, c_a, g_x0, g_dxdt); };
@@ -736,7 +448,6 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     ring.init(ring_mem, tid);
     auto do_u = [&](int wi) {
         const MarchLane m = march_decode(p, g, wi, lane);
-        if (PART == PART_REST && in_interior(g, m.strip, m.chunk)) return;   // the LEAN kernel's item
         ring.bind(p, m, x0, dxp);
         const int n_it = g.R + 2;
         ring.begin_item(p, m.ys - 2, n_it + 1);
@@ -831,5 +542,4 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
         cp_async_wait<0>();
     };
     run_interleaved(warp0, nwarps, g.n_warp_items, PA == 0 ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
-    }
 }

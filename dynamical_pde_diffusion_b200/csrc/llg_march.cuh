@@ -15,10 +15,11 @@
 //   * the VJP keeps a second three-row window of the field gradient G_H = d loss / d H_eff and emits row j - 1 while it
 //     evaluates row j: K^T G_H needs no shared tile, no barrier and no recomputed ring (only the two halo lanes of a
 //     60-column strip repeat work: 6 %);
-//   * interior work items (full chunks away from the grid boundary, strips without an edge column) run a lean loop with
-//     compile-time ring slots and running row pointers in their own LEAN kernel; the rest runs the same loop with
-//     reflected row offsets, edge selects and per-row validity (template flag) in the REST kernel, together with the
-//     a-plane streaming items and the reduction epilogue -- see "Three kernels" in heat_march.cuh for the rationale;
+//   * interior work items (full chunks away from the grid boundary, strips without an edge column) run a lean instantiation
+//     of the loop (running row offsets, no reflection, no edge selects, no per-row validity), the others the general one
+//     (template flag) -- both in ONE kernel, interleaved with the a-plane streaming items: splitting the pass into a lean
+//     and a general kernel was measured slower (0.51 ms vs 0.41 ms, reduce pass), the two halves are each latency-bound
+//     and only overlap inside one kernel;
 //   * the algebra is arranged for the fp64 pipe (the VJP needs ~100 fp64 instructions per pixel, as long as its 60 B of
 //     HBM traffic): r = dmdt + tau gamma a + tau alpha m x a;  with q = r x m and t = gamma r + alpha q:
 //     G_H = -gamma q - alpha q x m,  G_m = -(H x t) - alpha a x r;  the seed coefficient c_p multiplies the sums once.
@@ -35,9 +36,8 @@ __host__ __device__ constexpr int llg_ring_bytes() { return kLlgFields * kLR * k
 struct LlgMarchGeom {
     MarchGeom a;                             // a-plane streaming fields (a_plane4, a_block4, n_a_items, ...)
     int strips, R, chunks, n_items;          // u work item = (b innermost, strip, chunk)
-    // interior rectangle (strips s_lo..s_hi x chunks c_lo..c_hi; n_int_items == 0: none) -> LEAN kernel, the rest -> REST
-    // kernel (heat_march.cuh, "Three kernels"); part_base: first partial slot of the REST kernel
-    int s_lo, s_hi, c_lo, c_hi, n_int_items, part_base;
+    // interior rectangle (strips s_lo..s_hi x chunks c_lo..c_hi; n_int_items == 0: none): its items take the lean loop
+    int s_lo, s_hi, c_lo, c_hi, n_int_items;
 };
 
 struct LlgLane {
@@ -49,21 +49,14 @@ __device__ __forceinline__ bool llg_in_interior(const LlgMarchGeom& g, int strip
     return g.n_int_items > 0 && strip >= g.s_lo && strip <= g.s_hi && chunk >= g.c_lo && chunk <= g.c_hi;
 }
 
-// LEAN: `item` indexes the interior rectangle; otherwise the full (b, strip, chunk) space.  `skip`: REST kernel and the
-// item belongs to the LEAN kernel.
-template <bool LEAN>
-__device__ __forceinline__ LlgLane llg_lane_decode(const Params& p, const LlgMarchGeom& g, int item, int lane, bool& skip) {
+// item -> lane geometry; `interior`: the item lies in the interior rectangle and takes the lean loop
+__device__ __forceinline__ LlgLane llg_lane_decode(const Params& p, const LlgMarchGeom& g, int item, int lane, bool& interior) {
     LlgLane m;
     const unsigned t = (unsigned)item / (unsigned)p.B;
     m.b = (int)((unsigned)item - t * p.B);
-    const unsigned ns = LEAN ? (unsigned)(g.s_hi - g.s_lo + 1) : (unsigned)g.strips;
-    unsigned chunk = t / ns;
-    int strip = (int)(t - chunk * ns);
-    if (LEAN) {
-        strip += g.s_lo;
-        chunk += g.c_lo;
-    }
-    skip = !LEAN && llg_in_interior(g, strip, (int)chunk);
+    const unsigned chunk = t / (unsigned)g.strips;
+    const int strip = (int)(t - chunk * g.strips);
+    interior = llg_in_interior(g, strip, (int)chunk);
     m.col0 = strip * kLlgStrip - 2 + 2 * lane;
     m.lane_ok = m.col0 >= 0 && m.col0 < p.W;
     m.out_ok = m.lane_ok && lane >= 1 && lane <= 30;
@@ -320,7 +313,7 @@ __device__ __forceinline__ void llg_march_reduce_item(const Params& p, const Llg
     }
 }
 
-template <bool HAS_D, bool HAS_O, int PART>
+template <bool HAS_D, bool HAS_O>
 __global__ void __launch_bounds__(kLlgThreads, 3)
 llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, double* __restrict__ partials,
                         unsigned int* __restrict__ ticket, double* __restrict__ sums, int finalize, double* __restrict__ scal,
@@ -331,29 +324,17 @@ llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
-    if constexpr (PART == PART_LEAN) {
-        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
-            bool skip;
-            const LlgLane m = llg_lane_decode<true>(p, g, idx, lane, skip);
+    auto do_a = [&](int item) { a_item_reduce(p, g.a, item, lane, s_a); };
+    auto do_u = [&](int item) {
+        bool interior;
+        const LlgLane m = llg_lane_decode(p, g, item, lane, interior);
+        if (interior)                                                  // warp-uniform: one strip per warp
             llg_march_reduce_item<HAS_D, HAS_O, true>(p, g, m, ring_mem, s_u, s_p);
-        }
-        block_sum3<kLlgThreads>(s_a, s_u, s_p, scratch);               // per-CTA partial -> slot; the REST kernel's last CTA adds them
-        if (tid == 0) {
-            partials[3 * blockIdx.x + 0] = 0.0;
-            partials[3 * blockIdx.x + 1] = s_u;
-            partials[3 * blockIdx.x + 2] = s_p;
-        }
-    } else {
-        auto do_a = [&](int item) { a_item_reduce(p, g.a, item, lane, s_a); };
-        auto do_u = [&](int item) {
-            bool skip;
-            const LlgLane m = llg_lane_decode<false>(p, g, item, lane, skip);
-            if (skip) return;                                          // the LEAN kernel's item (warp-uniform)
+        else
             llg_march_reduce_item<HAS_D, HAS_O, false>(p, g, m, ring_mem, s_u, s_p);
-        };
-        run_interleaved(warp0, nwarps, g.n_items, p.has_a ? g.a.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
-        reduce_epilogue_n<kLlgThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace, g.part_base);
-    }
+    };
+    run_interleaved(warp0, nwarps, g.n_items, p.has_a ? g.a.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+    reduce_epilogue_n<kLlgThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -485,8 +466,9 @@ __device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMar
     cp_async_wait<0>();
 }
 
-template <bool HAS_D, bool HAS_O, int PART>
-__global__ void __launch_bounds__(kLlgThreads, 3)
+// two CTAs per SM: the loop needs ~246 registers; at 168 (three CTAs) it spills and runs 0.96 ms instead of 0.86 ms (8 x 6 x 2048^2)
+template <bool HAS_D, bool HAS_O>
+__global__ void __launch_bounds__(kLlgThreads, 2)
 llg_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, const double* __restrict__ scal,
                      const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
     extern __shared__ __align__(16) unsigned char ring_mem[];
@@ -494,20 +476,14 @@ llg_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ L
     const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
     const double up = upstream ? __ldg(upstream) : 1.0;
     const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
-    if constexpr (PART == PART_LEAN) {
-        for (int idx = warp0; idx < g.n_int_items; idx += nwarps) {
-            bool skip;
-            const LlgLane m = llg_lane_decode<true>(p, g, idx, lane, skip);
+    auto do_a = [&](int item) { a_item_vjp(p, g.a, item, lane, c_a, g_x0, g_dxdt); };
+    auto do_u = [&](int item) {
+        bool interior;
+        const LlgLane m = llg_lane_decode(p, g, item, lane, interior);
+        if (interior)                                                  // (the host leaves the rectangle empty when g_dxdt is wanted)
             llg_march_vjp_item<HAS_D, HAS_O, true>(p, g, m, ring_mem, c_u, c_p, g_x0, nullptr);
-        }
-    } else {
-        auto do_a = [&](int item) { a_item_vjp(p, g.a, item, lane, c_a, g_x0, g_dxdt); };
-        auto do_u = [&](int item) {
-            bool skip;
-            const LlgLane m = llg_lane_decode<false>(p, g, item, lane, skip);
-            if (skip) return;
+        else
             llg_march_vjp_item<HAS_D, HAS_O, false>(p, g, m, ring_mem, c_u, c_p, g_x0, g_dxdt);
-        };
-        run_interleaved(warp0, nwarps, g.n_items, g.a.n_a_items, (tid >> 5) & 1, do_u, do_a);
-    }
+    };
+    run_interleaved(warp0, nwarps, g.n_items, g.a.n_a_items, (tid >> 5) & 1, do_u, do_a);
 }

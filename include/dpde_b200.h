@@ -93,9 +93,11 @@ int dpde_set_fast_path(int enable);
 /* Experiment knobs of the row-marching kernels (results never change, only speed): key 0 strip layout (0 (default) =
    per pass: 120 columns + 1 halo lane in the reduce pass, 112 + 2 sector aligned in the VJP; 1 / 2 force one of them), key 2 rows per chunk (0 = automatic: up to 128 in the
    VJP, 64 in the reduce pass), keys 3 / 4 = 1 pair every a-plane with the u-plane of the same index in the reduce /
-   VJP pass instead of streaming it as separate work items, key 5 = 1 sends interior work items through the general
-   loops instead of the lean interior loops (A/B measurements).  TEST / TUNING HOOK like dpde_set_fast_path: process-wide
-   atomics; the per-stream thread-safety of the compute entry points does not extend to changing these concurrently. */
+   VJP pass instead of streaming it as separate work items, key 5 = 1 sends the interior work items of the LLG marching kernels
+   through their general loop (A/B measurements of the lean loop), key 6 selects the LLG m x H_eff kernels: 0 (default) =
+   row-marching kernels on large grids (W >= 128, >= 4 Mi pixels), convert-once tiles otherwise; 1 = tiles always; 2 = marching
+   whenever W >= 128.  TEST / TUNING HOOK like dpde_set_fast_path: process-wide atomics; the per-stream thread-safety of the
+   compute entry points does not extend to changing these concurrently. */
 int dpde_set_tuning(int key, int value);
 
 /* Bytes of scratch the reduce pass needs (per-CTA partial sums + a ticket counter).  The caller zero-fills it

@@ -2,7 +2,7 @@
 `scripts/sanitize.sh` is kept for pools where it is open).  What memcheck / racecheck would look for is provoked directly:
 
 * out-of-bounds WRITES: every output lives in the middle of a larger allocation filled with a canary bit pattern; the
-  canaries on both sides must survive every kernel (generic tiles, marching loops incl. the lean interior loops, LLG tiles,
+  canaries on both sides must survive every kernel (generic tiles, heat and LLG marching loops incl. the lean interior loop, LLG tiles,
   streaming updates, the slab variants that must leave ghost rows alone);
 * out-of-bounds READS that matter: every input lives between NaN guard bands; any stray read that reaches an output or a
   sum turns it into NaN, and the results must equal the run on plain tensors bit for bit;
@@ -76,7 +76,7 @@ def _case(kind, B, ch_a, cu, H, W, seed):
 
 
 SHAPES = [("heat", 2, 1, 1, 37, 130), ("heat", 1, 1, 1, 100, 520), ("heat", 3, 1, 1, 16, 12), ("heat", 2, 0, 1, 64, 256),
-          ("llg_residual", 2, 3, 3, 33, 68), ("llg_residual", 1, 3, 3, 64, 16), ("llg_norm", 2, 3, 3, 40, 132)]
+          ("llg_residual", 2, 3, 3, 33, 68), ("llg_residual", 1, 3, 3, 64, 16), ("llg_residual", 2, 3, 3, 40, 260), ("llg_norm", 2, 3, 3, 40, 132)]
 
 
 @pytest.mark.parametrize("case", SHAPES, ids=lambda c: f"{c[0]}-{c[1]}x{c[2] + c[3]}x{c[4]}x{c[5]}")
@@ -86,8 +86,8 @@ def test_guidance_kernels_respect_their_buffers_and_reproduce(case, rows, kernel
     from dynamical_pde_diffusion_b200._ffi import PDE_HEAT, PDE_LLG_NORM, PDE_LLG_RESIDUAL
 
     kind, B, ch_a, cu, H, W = case
-    if rows and (kind != "heat" or kernel_path != "march"):
-        pytest.skip("chunk length only concerns the heat marching kernels")
+    if rows and (kind == "llg_norm" or kernel_path != "march"):
+        pytest.skip("chunk length only concerns the marching kernels")
     code = {"heat": PDE_HEAT, "llg_residual": PDE_LLG_RESIDUAL, "llg_norm": PDE_LLG_NORM}[kind]
     x0, dxdt, obs_a, obs_u, mask_a, mask_u, coef = _case(kind, B, ch_a, cu, H, W, seed=H * 7 + W)
     dev, w = _dev(), (20.0, 0.5, 20.0)
@@ -111,6 +111,7 @@ def test_guidance_kernels_respect_their_buffers_and_reproduce(case, rows, kernel
     try:
         if rows:
             _ffi.check(_ffi.lib().dpde_set_tuning(2, rows))
+            _ffi.check(_ffi.lib().dpde_set_tuning(6, 2))      # LLG residual: the marching kernels also on these small grids
         plain = engine(lambda t: t.to(dev))
         g_ref, _ = plain.seed(x0.to(dev), dxdt.to(dev) if use_d else None, w)
         s_ref = plain.scalars.clone()
@@ -131,6 +132,7 @@ def test_guidance_kernels_respect_their_buffers_and_reproduce(case, rows, kernel
     finally:
         if rows:
             _ffi.check(_ffi.lib().dpde_set_tuning(2, 0))
+            _ffi.check(_ffi.lib().dpde_set_tuning(6, 0))
 
 
 @pytest.mark.parametrize("n", [1, 5, 1023, 4100, 2 * 2 * 64 * 64 + 3])

@@ -203,48 +203,6 @@ def test_tuning_knobs_never_change_results(tune):
     assert _ffi.lib().dpde_set_tuning(99, 0) != 0
 
 
-@pytest.mark.parametrize("shape", [(2, 1, 1, 100, 520), (1, 1, 2, 76, 400), (2, 0, 1, 64, 1024)])
-@pytest.mark.parametrize("rows", [8, 16, 14, 30])
-@pytest.mark.parametrize("obs", [True, False])
-def test_heat_interior_loops_match_closed_form(shape, rows, obs):
-    """The lean interior loops of the marching kernels (full chunks away from the grid boundary, strips without an
-    edge column): chunk lengths that make the reduce pass (8, 16) resp. the VJP (14, 30: R + 2 a multiple of its ring
-    depth) take them on these small grids, against the closed form and against the general loops (tuning key 5)."""
-    from dynamical_pde_diffusion_b200 import GuidanceEngine, _ffi
-    from dynamical_pde_diffusion_b200._ffi import PDE_HEAT
-
-    B, ch_a, cu, H, W = shape
-    x0, dxdt, labels, obs_a, obs_u, mask_a, mask_u = _heat_case(B, max(ch_a, 1), cu, H, W, seed=H + W + rows)
-    if ch_a == 0:
-        x0, dxdt = x0[:, 1:].contiguous(), dxdt[:, 1:].contiguous()
-    if not obs:
-        mask_u = torch.zeros_like(mask_u)
-    dx, w, dev = 1.0 / (H - 1), (20.0, 0.5, 20.0), _dev()
-
-    def run():
-        eng = GuidanceEngine(B, ch_a + cu, ch_a, H, W, PDE_HEAT, dev, obs_a=obs_a.to(dev) if ch_a else None,
-                             mask_a=mask_a.to(dev) if ch_a else None, obs_u=obs_u.to(dev), mask_u=mask_u.to(dev),
-                             sample_coef=labels[:, -1].double().to(dev), dx=dx)
-        g, _ = eng.seed(x0.to(dev), dxdt.to(dev), w)
-        return eng.scalars[:4].clone(), g
-
-    try:
-        _ffi.check(_ffi.lib().dpde_set_tuning(2, rows))
-        s_lean, g_lean = run()
-        _ffi.check(_ffi.lib().dpde_set_tuning(5, 1))
-        s_gen, g_gen = run()
-    finally:
-        _ffi.check(_ffi.lib().dpde_set_tuning(2, 0))
-        _ffi.check(_ffi.lib().dpde_set_tuning(5, 0))
-    oa, ma = (np.asarray(obs_a, np.float64), np.asarray(mask_a, np.float64)) if ch_a else (np.zeros((B, 0, H, W)), np.zeros((H, W)))
-    losses, g_ref, _ = R.heat_guidance_numpy(x0.double().numpy(), dxdt.double().numpy(), labels[:, -1].double().numpy(), dx, oa,
-                                             obs_u.double().numpy(), ma, mask_u.double().numpy(), ch_a, *w)
-    _close(s_lean, np.array(losses), 1e-12, "losses (lean loops)")
-    _close(g_lean, g_ref, RTOL32, "seed gradient (lean loops)")
-    _close(s_gen, s_lean, 1e-13, "losses, general vs lean loops")
-    _close(g_gen, g_lean, 2e-7, "seed gradient, general vs lean loops")
-
-
 def test_heat_guidance_fp64_fields_and_autograd_cross_check():
     """fp64 fields (what the unmodified sampler holds) and an independent check against torch autograd on the device."""
     from dynamical_pde_diffusion_b200 import GuidanceEngine
@@ -350,6 +308,68 @@ def test_llg_residual_guidance(shape, K0, kernel_path):
     _close(eng.scalars[2], np.array(loss), 1e-12, "llg residual loss")
     _close(g[:, ch_a:], gm_ref, RTOL32, "llg residual seed")
     _close(gd[:, ch_a:], gd_ref, RTOL32, "llg residual d/d dmdt")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 40, 132), (1, 3, 70, 260), (2, 0, 36, 128), (1, 3, 33, 520)])
+@pytest.mark.parametrize("rows", [0, 8, 6, 14])
+@pytest.mark.parametrize("want_d", [False, True])
+def test_llg_residual_marching_kernels(shape, rows, want_d):
+    """The row-marching LLG kernels (llg_march.cuh; default on large grids only) forced onto small grids by tuning key 6 = 2:
+    against the closed form, with chunk lengths that give the reduce pass (8) resp. the VJP (6, 14: R + 2 a multiple of the
+    ring depth) interior work items for the lean loop, with and without the d / d dmdt output (which disables the lean VJP
+    loop), with K0 != 0, and against the tile kernels (key 6 = 1) and the general loop only (key 5 = 1)."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_LLG_RESIDUAL
+
+    B, ch_a, H, W = shape
+    gen = torch.Generator().manual_seed(3 * H + W + rows)
+    x0 = torch.randn(B, ch_a + 3, H, W, generator=gen)
+    m = x0[:, ch_a:]
+    x0[:, ch_a:] = m / m.norm(dim=1, keepdim=True) * (1 + 0.05 * torch.randn(B, 1, H, W, generator=gen))
+    dxdt = 0.01 * torch.randn(B, ch_a + 3, H, W, generator=gen)
+    field = (30 * torch.randn(B, 3, generator=gen)).double()
+    obs_u, mask_u = torch.randn(1, 3, H, W, generator=gen), torch.rand(3, H, W, generator=gen) < 0.2
+    obs_a, mask_a = torch.randn(1, max(ch_a, 1), H, W, generator=gen), torch.rand(H, W, generator=gen) < 0.3
+    dev, w, dx = _dev(), (10.0, 0.5, 10.0), 500e-9 / 64
+    K0 = 5e4 if rows == 6 else 0.0
+    c, rc = LLGConstants(K0=K0, easy_axis=(0.6, 0.0, 0.8)), R.LLGConstants(K0=K0, easy_axis=(0.6, 0.0, 0.8))
+
+    def run():
+        eng = GuidanceEngine(B, ch_a + 3, ch_a, H, W, PDE_LLG_RESIDUAL, dev, obs_a=obs_a.to(dev) if ch_a else None,
+                             mask_a=mask_a.to(dev) if ch_a else None, obs_u=obs_u.to(dev), mask_u=mask_u.to(dev),
+                             sample_coef=(field / (1000 * c.mu0)).to(dev), dx=dx, llg=c)
+        g, gd = eng.seed(x0.to(dev), dxdt.to(dev), w, want_dxdt_grad=want_d)
+        return eng.scalars[:4].clone(), g, gd
+
+    T = _ffi.lib().dpde_set_tuning
+    try:
+        _ffi.check(T(2, rows))
+        _ffi.check(T(6, 2))
+        s_m, g_m, gd_m = run()                    # marching, lean loop where the geometry allows it
+        _ffi.check(T(5, 1))
+        s_g, g_g, gd_g = run()                    # marching, general loop only
+        _ffi.check(T(5, 0))
+        _ffi.check(T(6, 1))
+        _ffi.check(T(2, 0))
+        s_t, g_t, gd_t = run()                    # convert-once tiles
+    finally:
+        for k in (2, 5, 6):
+            _ffi.check(T(k, 0))
+    loss, gm_ref, gd_ref = R.llg_residual_guidance_numpy(x0[:, ch_a:].double().numpy(), dxdt[:, ch_a:].double().numpy(),
+                                                         field.numpy(), dx, rc, w_pde=w[2])
+    mu = np.broadcast_to(mask_u.double().numpy(), (B, 3, H, W))
+    du = mu * (x0[:, ch_a:].double().numpy() - obs_u.double().numpy())
+    gm_ref = gm_ref + w[1] * mu * du / math.sqrt((du ** 2).sum())
+    _close(s_m[2], np.array(loss), 1e-12, "loss (marching)")
+    _close(g_m[:, ch_a:], gm_ref, RTOL32, "seed (marching)")
+    _close(s_g, s_m, 1e-13, "losses, general vs lean loop")
+    _close(g_g, g_m, 2e-7, "seed, general vs lean loop")
+    _close(s_t, s_m, 1e-12, "losses, tiles vs marching")
+    _close(g_t, g_m, 4e-7, "seed, tiles vs marching")
+    if want_d:
+        _close(gd_m[:, ch_a:], gd_ref, RTOL32, "d/d dmdt (marching)")
+        assert torch.all(gd_m[:, :ch_a] == 0)
+        _close(gd_t, gd_m, 4e-7, "d/d dmdt, tiles vs marching")
 
 
 @pytest.mark.parametrize("kind_name", ["heat", "llg_residual"])
