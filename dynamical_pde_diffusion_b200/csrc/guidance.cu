@@ -1022,9 +1022,20 @@ LlgMarchGeom llg_march_geometry(const Params& p, bool vjp, bool lean_ok) {
 }
 
 template <typename K>
-int llg_march_grid(K kernel, int64_t warp_items) {
+int llg_march_grid(K kernel, int64_t warp_items, int smem) {
+    static thread_local const void* configured[16][8] = {{nullptr}};   // > 48 KB opt-in, per device, as in march_occupancy
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto& mine = configured[dev & 15];
+    bool seen = false;
+    for (const void* k : mine) seen = seen || k == (const void*)kernel;
+    if (!seen || dev > 15) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (auto& k : mine)
+            if (!k) { k = (const void*)kernel; break; }
+    }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLlgThreads, llg_ring_bytes()) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLlgThreads, smem) != cudaSuccess || occ < 1) occ = 1;
     const int64_t need = (warp_items + kLlgThreads / 32 - 1) / (kLlgThreads / 32);
     return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials);
 }
@@ -1034,7 +1045,7 @@ int launch_llg_march_reduce(const Params& p, double* partials, unsigned int* tic
                             cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, false, true);
     auto k = llg_march_reduce_kernel<HAS_D, HAS_O>;
-    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes(false)), kLlgThreads, llg_smem_bytes(false), s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
     return check_launch("dpde_guidance_reduce (llg march)");
 }
 
@@ -1042,7 +1053,7 @@ template <bool HAS_D, bool HAS_O>
 int launch_llg_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, true, g_dxdt == nullptr);
     auto k = llg_march_vjp_kernel<HAS_D, HAS_O>;
-    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items), kLlgThreads, llg_ring_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes(true)), kLlgThreads, llg_smem_bytes(true), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
     return check_launch("dpde_guidance_vjp (llg march)");
 }
 

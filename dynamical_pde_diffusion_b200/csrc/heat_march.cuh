@@ -303,6 +303,107 @@ __device__ __forceinline__ void a_item_vjp(const Params& p, const MarchGeom& g, 
         for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pgd + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ---- the same items streamed through the (otherwise idle) per-lane cp.async ring of the marching kernels --------------
+// ncu of the LDG form inside the marching kernels: a third of all stall samples sat on the first use of an a-plane load
+// (each warp loads a block, waits ~1-2 us for it, computes, loads the next: nothing in flight while it computes).  Here
+// every lane keeps D float4 triples (a, obs, mask) in flight all the time: slot j is refilled with element t + D as soon as
+// element t has been read, exactly like the row ring of the u items.  NT = threads per CTA; `sbase` = shared-window address
+// of the ring memory (needs NT * D * 36 bytes).
+// Slot ownership: the ring memory is shared by all warps of the CTA while OTHER warps run u items, so a lane may only use
+// bytes that belong to it in the u-item ring too.  KF = index of the 16-byte field whose region the 4-byte mask slots
+// follow: the heat rings (RowRing: u | dudt | obs | masks, D = ring depth) map a -> u slots, obs -> dudt slots, mask -> mask
+// slots with KF = 3; a dedicated region (LLG kernels) packs a | obs | mask with KF = 2.
+template <int D, int NT, int KF>
+struct ARing {
+    unsigned a0, o0, k0;
+    __device__ __forceinline__ ARing(unsigned sbase) : a0(sbase + threadIdx.x * 16), o0(a0 + D * NT * 16), k0(sbase + KF * D * NT * 16 + threadIdx.x * 4) {}
+    __device__ __forceinline__ unsigned A(int s) const { return a0 + (unsigned)(s % D) * (NT * 16); }
+    __device__ __forceinline__ unsigned O(int s) const { return o0 + (unsigned)(s % D) * (NT * 16); }
+    __device__ __forceinline__ unsigned K(int s) const { return k0 + (unsigned)(s % D) * (NT * 4); }
+};
+
+template <int D, int NT, int KF, typename F>
+__device__ __forceinline__ void a_item_stream(const AItem& a, int lane, unsigned sbase, const float* pa, const float* po, const unsigned char* pm,
+                                              F&& consume) {
+    const ARing<D, NT, KF> r(sbase);
+    const int T = (a.n4 + 31) >> 5;                                   // iterations of the warp; lane's element of iteration t: lane + 32 t
+    auto issue = [&](int slot, int t) {
+        const int i = lane + 32 * t;
+        if (i < a.n4) {
+            cp_async16(r.A(slot), pa + 4 * i);
+            cp_async16(r.O(slot), po + 4 * i);
+            cp_async4(r.K(slot), pm + 4 * i);
+        }
+        cp_async_commit();
+    };
+    static_for<D>([&](auto J) { issue(decltype(J)::value, decltype(J)::value); });
+    const int groups = (T + D - 1) / D;
+#pragma unroll 1
+    for (int gi = 0; gi < groups; ++gi) {
+        static_for<D>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            const int t = gi * D + j, i = lane + 32 * t;
+            cp_async_wait<D - 1>();                                   // element t has landed
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), o = v;
+            unsigned k = 0u;
+            if (i < a.n4) {
+                v = lds128(r.A(j));
+                o = lds128(r.O(j));
+                k = lds32(r.K(j));
+            }
+            issue(j, t + D);                                          // element t + D -> the slot just drained
+            if (i < a.n4) consume(i, v, o, k);
+        });
+    }
+    cp_async_wait<0>();
+}
+
+template <int D, int NT, int KF>
+__device__ __forceinline__ void a_item_reduce_ring(const Params& p, const MarchGeom& g, int item, int lane, unsigned sbase, double& s_a) {
+    const AItem a = a_decode(p, g, item);
+    const int base = p.ylo * p.W + 4 * a.first4;
+    const float* pa = reinterpret_cast<const float*>(p.x0.p) + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
+    const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
+    const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
+    double s0 = 0.0, s1 = 0.0;
+    a_item_stream<D, NT, KF>(a, lane, sbase, pa, po, pm, [&](int, const float4& v, const float4& o, unsigned k) {
+        const double d0 = (double)v.x - (double)(sel_obs(k & 0xffu, o.x, v.x)), d1 = (double)v.y - (double)(sel_obs(k & 0xff00u, o.y, v.y));
+        const double d2 = (double)v.z - (double)(sel_obs(k & 0xff0000u, o.z, v.z)), d3 = (double)v.w - (double)(sel_obs(k & 0xff000000u, o.w, v.w));
+        s0 = fma(d0, d0, s0);
+        s1 = fma(d1, d1, s1);
+        s0 = fma(d2, d2, s0);
+        s1 = fma(d3, d3, s1);
+    });
+    s_a += s0 + s1;
+}
+
+template <int D, int NT, int KF>
+__device__ __forceinline__ void a_item_vjp_ring(const Params& p, const MarchGeom& g, int item, int lane, unsigned sbase, double c_a,
+                                                float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    if (!p.has_a) {                                                   // empty mask: zeros, nothing to read (sample.py:337-342)
+        a_item_vjp(p, g, item, lane, c_a, g_x0, g_dxdt);
+        return;
+    }
+    const AItem a = a_decode(p, g, item);
+    const int base = p.ylo * p.W + 4 * a.first4;
+    const int64_t plane = (int64_t)p.H * p.W;
+    float* pg = g_x0 + ((int64_t)a.b * p.C + a.ch) * plane + base;
+    float* pgd = g_dxdt ? g_dxdt + ((int64_t)a.b * p.C + a.ch) * plane + base : nullptr;
+    const float* pa = reinterpret_cast<const float*>(p.x0.p) + (int64_t)a.b * p.x0.sb + (int64_t)a.ch * p.x0.sc + base;
+    const float* po = reinterpret_cast<const float*>(p.obs_a.p) + (int64_t)a.b * p.obs_a.sb + (int64_t)a.ch * p.obs_a.sc + base;
+    const unsigned char* pm = reinterpret_cast<const unsigned char*>(p.mask_a.p) + (int64_t)a.b * p.mask_a.sb + (int64_t)a.ch * p.mask_a.sc + base;
+    a_item_stream<D, NT, KF>(a, lane, sbase, pa, po, pm, [&](int i, const float4& v, const float4& o, unsigned k) {
+        float4 w;
+        w.x = (float)(c_a * ((double)v.x - (double)(sel_obs(k & 0xffu, o.x, v.x))));
+        w.y = (float)(c_a * ((double)v.y - (double)(sel_obs(k & 0xff00u, o.y, v.y))));
+        w.z = (float)(c_a * ((double)v.z - (double)(sel_obs(k & 0xff0000u, o.z, v.z))));
+        w.w = (float)(c_a * ((double)v.w - (double)(sel_obs(k & 0xff000000u, o.w, v.w))));
+        *reinterpret_cast<float4*>(pg + 4 * i) = w;
+    });
+    if (pgd)
+        for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pgd + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Each warp owns every nwarps-th u-item (compute/issue bound) and a-item (pure streaming, latency bound) and
 // alternates between the two kinds in proportion, odd warps starting with the other kind, so that at any time an
 // SM runs a mix of both and the streaming warps' memory stalls overlap the marching warps' arithmetic.
@@ -345,6 +446,8 @@ heat_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
 
     // ---- a-planes: sum (mask (a - obs))^2; a warp streams one block of a plane with 128-bit loads
+    // (LDG form: this pass's ring is 4 deep, shallower than the eight loads per lane the LDG form keeps in flight -- measured
+    //  0.370 ms streamed through the ring vs 0.320 ms)
     auto do_a = [&](int item) { a_item_reduce(p, g, item, lane, s_a); };
 
     // ---- u-planes: iteration `it` handles row j = ys + it with the window ua = u[j-1], ub = u[j], uc = u[j+1].
@@ -437,7 +540,7 @@ heat_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ 
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
 
     // ---- a-planes: g = c_a mask (mask (a - obs)), zeros when the mask is empty (sample.py:337-342)
-    auto do_a = [&](int item) { a_item_vjp(p, g, item, lane, c_a, g_x0, g_dxdt); };
+    auto do_a = [&](int item) { a_item_vjp_ring<ring_depth(0, true), kThreads, 3>(p, g, item, lane, (unsigned)__cvta_generic_to_shared(ring_mem), c_a, g_x0, g_dxdt); };
 
     // ---- u-planes.  Iteration `it` computes the residual of row j = ys - 1 + it (window ua = u[j-1], ub = u[j],
     //      uc = u[j+1]) and then emits the gradient of row jo = j - 1 from r2 = r[jo-1], r1 = r[jo], r0 = r[jo+1].

@@ -28,10 +28,13 @@
 // Eligibility (host): as llg_tile.cuh (fp32 fields, W % 4 == 0, aligned bases, fp32 observations, uint8 masks) and W >= 128.
 
 constexpr int kLR = 4;                       // ring depth (rows per lane in flight)
-constexpr int kLlgThreads = 128;             // 4 warps per CTA: three CTAs share an SM at <= 170 registers
+constexpr int kLlgThreads = 128;             // 4 warps per CTA (reduce pass: four CTAs per SM at 128 registers; VJP: two at ~246)
 constexpr int kLlgFields = 9;                // m[3], dmdt[3], obs[3] -- 8 bytes per lane and row each
 constexpr int kLlgStrip = 60;                // output columns per warp strip (+ one 2-column halo lane per side)
 __host__ __device__ constexpr int llg_ring_bytes() { return kLlgFields * kLR * kLlgThreads * 8; }
+constexpr int kLlgAD = 8;                    // a-plane items: float4 triples per lane in flight (own region behind the row ring)
+__host__ __device__ constexpr int llg_aring_bytes() { return kLlgAD * kLlgThreads * 36; }
+__host__ __device__ constexpr int llg_smem_bytes(bool vjp) { return llg_ring_bytes() + (vjp ? llg_aring_bytes() : 0); }
 
 struct LlgMarchGeom {
     MarchGeom a;                             // a-plane streaming fields (a_plane4, a_block4, n_a_items, ...)
@@ -313,8 +316,10 @@ __device__ __forceinline__ void llg_march_reduce_item(const Params& p, const Llg
     }
 }
 
+// four CTAs per SM (128 registers, a few spills outside the row loop): measured 0.386 ms against 0.403 ms at three CTAs / 168
+// registers and 0.551 ms at five / 96 (8 x 6 x 2048^2) -- the pass is latency-bound, occupancy pays until the spills reach the loop
 template <bool HAS_D, bool HAS_O>
-__global__ void __launch_bounds__(kLlgThreads, 3)
+__global__ void __launch_bounds__(kLlgThreads, 4)
 llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, double* __restrict__ partials,
                         unsigned int* __restrict__ ticket, double* __restrict__ sums, int finalize, double* __restrict__ scal,
                         float* __restrict__ trace) {
@@ -476,7 +481,7 @@ llg_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ L
     const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
     const double up = upstream ? __ldg(upstream) : 1.0;
     const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
-    auto do_a = [&](int item) { a_item_vjp(p, g.a, item, lane, c_a, g_x0, g_dxdt); };
+    auto do_a = [&](int item) { a_item_vjp_ring<kLlgAD, kLlgThreads, 2>(p, g.a, item, lane, (unsigned)__cvta_generic_to_shared(ring_mem) + llg_ring_bytes(), c_a, g_x0, g_dxdt); };
     auto do_u = [&](int item) {
         bool interior;
         const LlgLane m = llg_lane_decode(p, g, item, lane, interior);
