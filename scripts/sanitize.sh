@@ -8,6 +8,7 @@
 #   synccheck  divergent / invalid barrier use (the tile kernels' early-outs around __syncthreads)
 #   initcheck  (optional, TOOLS="... initcheck") reads of uninitialised global memory; noisy under the torch caching allocator
 #
+# One tool per gpurun call: TOOLS=memcheck scripts/sanitize.sh r2 (then racecheck, synccheck in their own calls).
 # usage: scripts/sanitize.sh <tag>      -> gpurun_out/<tag>_sanitize_<tool>.log + gpurun_out/<tag>_sanitize_summary.txt
 tag=${1:-r2}
 O=gpurun_out
@@ -20,7 +21,7 @@ summary=$O/${tag}_sanitize_summary.txt
 echo "# compute-sanitizer over: pytest -m gpu -k \"$SEL\" $FILES" > $summary
 echo "# $($SAN --version | tail -1)" >> $summary
 rc_all=0
-for tool in ${TOOLS:-memcheck racecheck synccheck}; do
+for tool in ${TOOLS:-memcheck}; do
     log=$O/${tag}_sanitize_${tool}.log
     extra=""
     [ "$tool" = "memcheck" ] && extra="--leak-check no"
