@@ -1045,7 +1045,7 @@ int launch_llg_march_reduce(const Params& p, double* partials, unsigned int* tic
                             cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, false, true);
     auto k = llg_march_reduce_kernel<HAS_D, HAS_O>;
-    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes(false)), kLlgThreads, llg_smem_bytes(false), s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes()), kLlgThreads, llg_smem_bytes(), s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
     return check_launch("dpde_guidance_reduce (llg march)");
 }
 
@@ -1053,7 +1053,7 @@ template <bool HAS_D, bool HAS_O>
 int launch_llg_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, true, g_dxdt == nullptr);
     auto k = llg_march_vjp_kernel<HAS_D, HAS_O>;
-    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes(true)), kLlgThreads, llg_smem_bytes(true), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes()), kLlgThreads, llg_smem_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
     return check_launch("dpde_guidance_vjp (llg march)");
 }
 

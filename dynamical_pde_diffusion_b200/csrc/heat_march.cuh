@@ -316,7 +316,8 @@ __device__ __forceinline__ void a_item_vjp(const Params& p, const MarchGeom& g, 
 template <int D, int NT, int KF>
 struct ARing {
     unsigned a0, o0, k0;
-    __device__ __forceinline__ ARing(unsigned sbase) : a0(sbase + threadIdx.x * 16), o0(a0 + D * NT * 16), k0(sbase + KF * D * NT * 16 + threadIdx.x * 4) {}
+    // `t` = index of the thread among the NT threads that share the region (NT == 32: a warp-private region, t = lane)
+    __device__ __forceinline__ ARing(unsigned sbase, int t) : a0(sbase + t * 16), o0(a0 + D * NT * 16), k0(sbase + KF * D * NT * 16 + t * 4) {}
     __device__ __forceinline__ unsigned A(int s) const { return a0 + (unsigned)(s % D) * (NT * 16); }
     __device__ __forceinline__ unsigned O(int s) const { return o0 + (unsigned)(s % D) * (NT * 16); }
     __device__ __forceinline__ unsigned K(int s) const { return k0 + (unsigned)(s % D) * (NT * 4); }
@@ -325,7 +326,7 @@ struct ARing {
 template <int D, int NT, int KF, typename F>
 __device__ __forceinline__ void a_item_stream(const AItem& a, int lane, unsigned sbase, const float* pa, const float* po, const unsigned char* pm,
                                               F&& consume) {
-    const ARing<D, NT, KF> r(sbase);
+    const ARing<D, NT, KF> r(sbase, NT == 32 ? lane : (int)threadIdx.x);
     const int T = (a.n4 + 31) >> 5;                                   // iterations of the warp; lane's element of iteration t: lane + 32 t
     auto issue = [&](int slot, int t) {
         const int i = lane + 32 * t;

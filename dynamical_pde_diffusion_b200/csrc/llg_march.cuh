@@ -32,9 +32,13 @@ constexpr int kLlgThreads = 128;             // 4 warps per CTA (reduce pass: fo
 constexpr int kLlgFields = 9;                // m[3], dmdt[3], obs[3] -- 8 bytes per lane and row each
 constexpr int kLlgStrip = 60;                // output columns per warp strip (+ one 2-column halo lane per side)
 __host__ __device__ constexpr int llg_ring_bytes() { return kLlgFields * kLR * kLlgThreads * 8; }
-constexpr int kLlgAD = 8;                    // a-plane items: float4 triples per lane in flight (own region behind the row ring)
-__host__ __device__ constexpr int llg_aring_bytes() { return kLlgAD * kLlgThreads * 36; }
-__host__ __device__ constexpr int llg_smem_bytes(bool vjp) { return llg_ring_bytes() + (vjp ? llg_aring_bytes() : 0); }
+// The ring is WARP-MAJOR: warp w owns bytes [w, w + 1) * llg_warp_ring_bytes() (9216), element (field, slot) of a lane at
+// (field * kLR + slot) * 256 + lane * 8.  A warp runs either a u item or an a-plane item, so the a items stream through the
+// same 9216 bytes (ARing<kLlgAD, 32, 2>: 8 float4 triples a | obs | mask per lane in flight = 8 * 32 * 36 bytes exactly).
+__host__ __device__ constexpr int llg_warp_ring_bytes() { return kLlgFields * kLR * 32 * 8; }
+constexpr int kLlgAD = 8;
+static_assert(kLlgAD * 32 * 36 == llg_warp_ring_bytes(), "a-plane ring must fit the warp's row ring exactly");
+__host__ __device__ constexpr int llg_smem_bytes() { return llg_ring_bytes(); }
 
 struct LlgMarchGeom {
     MarchGeom a;                             // a-plane streaming fields (a_plane4, a_block4, n_a_items, ...)
@@ -71,6 +75,10 @@ __device__ __forceinline__ LlgLane llg_lane_decode(const Params& p, const LlgMar
     return m;
 }
 
+struct Mask3 {
+    unsigned k[3];
+};
+
 struct V6 {
     double v[3][2];                          // [component][pixel of the lane]
 };
@@ -83,7 +91,8 @@ __device__ __forceinline__ float2 lds64f(unsigned smem) {
 __device__ __forceinline__ void cp_async8(unsigned smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ unsigned llg_slot(int field, int s) { return (unsigned)((field * kLR + (s & (kLR - 1))) * kLlgThreads * 8); }
+__device__ __forceinline__ unsigned llg_slot(int field, int s) { return (unsigned)((field * kLR + (s & (kLR - 1))) * 32 * 8); }
+__device__ __forceinline__ unsigned llg_warp_ring(unsigned char* smem) { return (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * llg_warp_ring_bytes(); }
 
 // acc = fma(a, b, acc) where `bit` is non-zero: a test + select of the 64-bit result (ptxas turns a predicated DFMA into
 // the same DFMA + FSEL pair)
@@ -149,7 +158,7 @@ struct LlgRing {
     const unsigned char* pk[3];
 
     __device__ __forceinline__ void bind(const Params& p, const LlgLane& m, unsigned char* smem) {
-        base = (unsigned)__cvta_generic_to_shared(smem) + threadIdx.x * 8;
+        base = llg_warp_ring(smem) + (threadIdx.x & 31) * 8;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             pm[c] = reinterpret_cast<const float*>(p.x0.p) + (int64_t)m.b * p.x0.sb + (int64_t)(p.ch_a + c) * p.x0.sc + m.colc;
@@ -198,24 +207,20 @@ struct LlgRing {
         }
         return o;
     }
-    // the three components' two mask bytes of one row, packed: bit 0 of byte (2 c + i) = pixel i of component c observed
-    __device__ __forceinline__ uint2 masks(int64_t off) const {
-        unsigned lo = 0u, hi = 0u;
+    // the three components' two mask bytes of one row, as loaded: bit 0 of byte i of k[c] = pixel i of component c observed.
+    // The words are NOT combined here: they are fetched one row ahead and any arithmetic on them at the load site would
+    // wait for the load (ncu, r2n: a quarter of the reduce pass's stall samples sat on exactly that combine).
+    __device__ __forceinline__ Mask3 masks(int64_t off) const {
+        Mask3 k{{0u, 0u, 0u}};
         if (HAS_O) {
-            const unsigned k0 = __ldg(reinterpret_cast<const unsigned short*>(pk[0] + off));
-            const unsigned k1 = __ldg(reinterpret_cast<const unsigned short*>(pk[1] + off));
-            const unsigned k2 = __ldg(reinterpret_cast<const unsigned short*>(pk[2] + off));
-            lo = k0 | (k1 << 16);
-            hi = k2;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) k.k[c] = __ldg(reinterpret_cast<const unsigned short*>(pk[c] + off));
         }
-        return make_uint2(lo, hi);
+        return k;
     }
 };
 
-__device__ __forceinline__ unsigned mask_bit(const uint2& k, int c, int i) {
-    const unsigned w = c < 2 ? k.x : k.y;
-    return w & (1u << (16 * (c & 1) + 8 * i));
-}
+__device__ __forceinline__ unsigned mask_bit(const Mask3& k, int c, int i) { return k.k[c] & (1u << (8 * i)); }
 
 // unscaled 5-point sums of one row for the lane's two columns of one component
 __device__ __forceinline__ void lap2(const double* up, const double* ct, const double* dn, double lf, double rt, double* s) {
@@ -244,7 +249,7 @@ __device__ __forceinline__ void llg_march_reduce_item(const Params& p, const Llg
 #pragma unroll
     for (int s = 0; s < kLR; ++s) ring.issue(s, off_of(s), s >= 1 && s <= n_it, s < n_it, s < n_it);
     V6 mu = ring.direct_m(off_of(-1)), mc = ring.direct_m(off_of(0));
-    uint2 mk = ring.masks(off_of(0));
+    Mask3 mk = ring.masks(off_of(0));
     double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
 
     auto row = [&](int it, auto J, bool refill_m, bool refill_f) {
@@ -253,7 +258,7 @@ __device__ __forceinline__ void llg_march_reduce_item(const Params& p, const Llg
         const V6 md = ring.get_m(j + 1);
         const V6 dt = ring.get_f(3, j, HAS_D), ob = ring.get_f(6, j, HAS_O);
         ring.issue(j, off_of(it + kLR), refill_m, refill_f, refill_f);
-        const uint2 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : make_uint2(0u, 0u);
+        const Mask3 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : Mask3{{0u, 0u, 0u}};
         double lap[3][2];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -329,7 +334,11 @@ llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
-    auto do_a = [&](int item) { a_item_reduce(p, g.a, item, lane, s_a); };
+    auto do_a = [&](int item) {
+        __syncwarp();
+        a_item_reduce_ring<kLlgAD, 32, 2>(p, g.a, item, lane, llg_warp_ring(ring_mem), s_a);
+        __syncwarp();
+    };
     auto do_u = [&](int item) {
         bool interior;
         const LlgLane m = llg_lane_decode(p, g, item, lane, interior);
@@ -371,7 +380,7 @@ __device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMar
     for (int s = 0; s < kLR; ++s) ring.issue(s, off_of(s), s >= 2 && s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
     V6 mu = ring.direct_m(off_of(0)), mc = ring.direct_m(off_of(1));
     V6 g2{}, g1{}, lp{};                                              // G_H[jo-1], G_H[jo], pointwise part of row jo
-    uint2 mk = make_uint2(0u, 0u);                                    // masks of the row emitted in THIS iteration
+    Mask3 mk{{0u, 0u, 0u}};                                           // masks of the row emitted in THIS iteration
     // column weights of the transposed stencil (general path): neighbour q counts twice when it lies on an edge column
     const double wl0 = LEAN ? 1.0 : (m.left_edge ? 0.0 : (m.col0 - 1 == 0 ? 2.0 : 1.0));        // left neighbour of pixel 0 (other lane)
     const double wl1 = LEAN ? 1.0 : (m.col0 == 0 ? 2.0 : 1.0);                                  // left neighbour of pixel 1 = pixel 0
@@ -385,7 +394,7 @@ __device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMar
         const V6 dt = ring.get_f(3, j + 1, HAS_D), ob = ring.get_f(6, j, HAS_O);
         ring.issue(j, off_of(it + kLR), refill_m, refill_d, refill_o);
         const int y = m.ys - 1 + it, jo = y - 1;                       // evaluated row, emitted row (local)
-        const uint2 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : make_uint2(0u, 0u);
+        const Mask3 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : Mask3{{0u, 0u, 0u}};
         // ---- forward + backward at row y
         double lap[3][2];
 #pragma unroll
@@ -481,7 +490,11 @@ llg_march_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ L
     const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
     const double up = upstream ? __ldg(upstream) : 1.0;
     const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
-    auto do_a = [&](int item) { a_item_vjp_ring<kLlgAD, kLlgThreads, 2>(p, g.a, item, lane, (unsigned)__cvta_generic_to_shared(ring_mem) + llg_ring_bytes(), c_a, g_x0, g_dxdt); };
+    auto do_a = [&](int item) {
+        __syncwarp();
+        a_item_vjp_ring<kLlgAD, 32, 2>(p, g.a, item, lane, llg_warp_ring(ring_mem), c_a, g_x0, g_dxdt);
+        __syncwarp();
+    };
     auto do_u = [&](int item) {
         bool interior;
         const LlgLane m = llg_lane_decode(p, g, item, lane, interior);
