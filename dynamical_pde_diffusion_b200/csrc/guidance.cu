@@ -762,10 +762,12 @@ inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>
 inline bool s4(const View& v) { return v.sb % 4 == 0 && v.sc % 4 == 0; }
 
 // Can the row-marching kernels take this problem?  (else the generic tile kernels run)
-// float4 per streaming work item: kABlock on large problems, halved until every SM has ~32 warps' worth of items
+// float4 per streaming work item: kABlock on large problems, halved until there is about one item per resident warp.  Not
+// further: an item of 32 k float4 keeps k loads per lane in flight, and on L2-resident problems (the bench workload:
+// 64 x 128^2 planes) a warp that walks through four 32-float4 items pays four dependent memory latencies instead of one.
 inline int stream_block4(int64_t plane4, int64_t planes) {
     int blk = kABlock;
-    const int64_t want = (int64_t)sm_count() * 32;
+    const int64_t want = (int64_t)sm_count() * 8;
     while (blk > 32 && ((plane4 + blk - 1) / blk) * planes < want) blk >>= 1;
     return blk;
 }

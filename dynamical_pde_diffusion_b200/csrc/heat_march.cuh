@@ -265,7 +265,11 @@ __device__ __forceinline__ void a_item_reduce(const Params& p, const MarchGeom& 
 #pragma unroll
         for (int t = 0; t < 8; ++t) body(i0 + 32 * t + lane);
     }
-    for (int i = i0 + lane; i < a.n4; i += 32) body(i);
+    if (i0 < a.n4) {                         // ragged tail / small items: the same eight loads, predicated, still issued together
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (i0 + 32 * t + lane < a.n4) body(i0 + 32 * t + lane);
+    }
     s_a += s0 + s1;
 }
 
@@ -295,7 +299,11 @@ __device__ __forceinline__ void a_item_vjp(const Params& p, const MarchGeom& g, 
 #pragma unroll
             for (int t = 0; t < 8; ++t) body(i0 + 32 * t + lane);
         }
-        for (int i = i0 + lane; i < a.n4; i += 32) body(i);
+        if (i0 < a.n4) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (i0 + 32 * t + lane < a.n4) body(i0 + 32 * t + lane);
+        }
     } else {
         for (int i = lane; i < a.n4; i += 32) *reinterpret_cast<float4*>(pg + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
