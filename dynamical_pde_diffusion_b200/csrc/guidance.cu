@@ -1070,9 +1070,9 @@ int launch_llg_reduce(const Params& p, double* partials, unsigned int* ticket, d
     }
     const LlgGeom L = llg_geometry(p);
     if (p.kind == DPDE_PDE_LLG_NORM) {
-        auto k = llg_norm_reduce_kernel;
         const int64_t items = ((int64_t)L.n_norm_items + L.g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
-        k<<<llg_grid(k, 0, items), kThreads, 0, s>>>(p, L.g, L.n_norm_items, partials, ticket, sums, finalize, scal, trace);
+        auto go = [&](auto k) { k<<<llg_grid(k, 0, items), kThreads, 0, s>>>(p, L.g, L.n_norm_items, partials, ticket, sums, finalize, scal, trace); };
+        if (p.has_u) go(llg_norm_reduce_kernel<true, 1>); else go(llg_norm_reduce_kernel<false, 1>);
         return check_launch("dpde_guidance_reduce (llg norm)");
     }
     switch (L.tw) {
@@ -1090,9 +1090,9 @@ int launch_llg_vjp(const Params& p, const double* scal, const double* upstream, 
     }
     const LlgGeom L = llg_geometry(p);
     if (p.kind == DPDE_PDE_LLG_NORM) {
-        auto k = llg_norm_vjp_kernel;
         const int64_t items = ((int64_t)L.n_norm_items + L.g.n_a_items + kThreads / 32 - 1) / (kThreads / 32);
-        k<<<llg_grid(k, 0, items), kThreads, 0, s>>>(p, L.g, L.n_norm_items, scal, upstream, g_x0, g_dxdt);
+        auto go = [&](auto k) { k<<<llg_grid(k, norm_ring_bytes(), items), kThreads, norm_ring_bytes(), s>>>(p, L.g, L.n_norm_items, scal, upstream, g_x0, g_dxdt); };
+        if (p.has_u) go(llg_norm_vjp_kernel<true>); else go(llg_norm_vjp_kernel<false>);
         return check_launch("dpde_guidance_vjp (llg norm)");
     }
     switch (L.tw) {

@@ -493,7 +493,71 @@ __device__ __forceinline__ void widen4(const float4& f, double* d) {
     d[0] = (double)f.x; d[1] = (double)f.y; d[2] = (double)f.z; d[3] = (double)f.w;
 }
 
-__global__ void __launch_bounds__(kThreads, 3)   // measured 8x6x2048^2: 0.277 / 0.215 / 0.233 ms at 2 / 3 / 4 CTAs per SM
+// The three magnetisation planes (+ their observations and mask words) of a norm item stream through a per-thread
+// cp.async ring: D elements (one float4 per plane and array) of every lane are in flight all the time, the slot an iteration
+// drains is refilled with element t + D at once (VJP pass; round 1 loaded at the point of use).  Region: D x kThreads x 108 bytes (m | obs | masks); a-plane items use the same bytes as an
+// ARing<3 D, kThreads, 2> (3 D x 36 bytes per thread = the same 108 D), a warp runs one kind of item at a time and a
+// thread only ever touches its own bytes.
+constexpr int kNormD = 3;
+__host__ __device__ constexpr int norm_ring_bytes() { return kNormD * kThreads * 108; }
+
+template <int D, bool HAS_O, typename F>
+__device__ __forceinline__ void norm_item_stream(int n4, int lane, unsigned sbase, const float* m0, int64_t scm, const float* po, int64_t sco,
+                                                 const unsigned char* pm, int64_t sck, F&& consume) {
+    const unsigned m_base = sbase + threadIdx.x * 16, o_base = m_base + D * 3 * kThreads * 16;
+    const unsigned k_base = sbase + 2 * D * 3 * kThreads * 16 + threadIdx.x * 4;
+    auto M = [&](int slot, int c) { return m_base + (unsigned)((slot * 3 + c) * kThreads * 16); };
+    auto O = [&](int slot, int c) { return o_base + (unsigned)((slot * 3 + c) * kThreads * 16); };
+    auto K = [&](int slot, int c) { return k_base + (unsigned)((slot * 3 + c) * kThreads * 4); };
+    const int T = (n4 + 31) >> 5;
+    auto issue = [&](int slot, int t) {
+        const int i = lane + 32 * t;
+        if (i < n4) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                cp_async16(M(slot, c), m0 + c * scm + 4 * i);
+                if (HAS_O) {
+                    cp_async16(O(slot, c), po + c * sco + 4 * i);
+                    cp_async4(K(slot, c), pm + c * sck + 4 * i);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    static_for<D>([&](auto J) { issue(decltype(J)::value, decltype(J)::value); });
+    const int groups = (T + D - 1) / D;
+#pragma unroll 1
+    for (int gi = 0; gi < groups; ++gi) {
+        static_for<D>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            const int t = gi * D + j, i = lane + 32 * t;
+            cp_async_wait<D - 1>();                                   // element t has landed
+            float4 mf[3], of[3];
+            unsigned kk[3] = {0u, 0u, 0u};
+            if (i < n4) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    mf[c] = lds128(M(j, c));
+                    if (HAS_O) {
+                        of[c] = lds128(O(j, c));
+                        kk[c] = lds32(K(j, c));
+                    }
+                }
+            }
+            issue(j, t + D);
+            if (i < n4) consume(i, mf, of, kk);
+        });
+    }
+    cp_async_wait<0>();
+}
+
+// The reduce pass keeps the LDG form with one element of the magnetisation prefetched in registers (PF = 1) at three CTAs per SM.
+// Measured on 8 x 6 x 2048^2 (profiles/r2w_probe_norm_reduce_pf.log, r2v_*, r2s_*): PF = 0 / 1 0.212 / 0.199 ms; PF = 2 / 3 need 128
+// registers, i.e. two CTAs per SM: 0.253 / 0.229 ms -- the pass wants resident warps more than loads in flight per warp; m (or m,
+// observations and masks) streamed through a cp.async ring: 0.248 (0.263) ms, slower, as in the heat reduce pass.  Without
+// a-planes the norm items alone take 0.129 ms (3.1 TB/s), the a-plane items the other 0.07 ms (~6 TB/s).
+template <bool HAS_O, int PF>
+__global__ void __launch_bounds__(kThreads, PF >= 2 ? 2 : 3)   // measured 8x6x2048^2: 0.277 / 0.215 / 0.233 ms at 2 / 3 / 4 CTAs per SM
 llg_norm_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, int n_items,
                        double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ sums,
                        int finalize, double* __restrict__ scal, float* __restrict__ trace) {
@@ -502,104 +566,136 @@ llg_norm_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
-    for (int item = warp0; item < n_items; item += nwarps) {
+    auto do_u = [&](int item) {
         const NormItem it = norm_decode(p, g, item);
         const int base = p.ylo * p.W + 4 * it.first4;
         const float* m0 = reinterpret_cast<const float*>(p.x0.p) + (int64_t)it.b * p.x0.sb + (int64_t)p.ch_a * p.x0.sc + base;
-        const float* po = p.has_u ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)it.b * p.obs_u.sb + base : nullptr;
-        const unsigned char* pm = p.has_u ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)it.b * p.mask_u.sb + base : nullptr;
-        // software pipeline: the next iteration's magnetisation is in flight while this one's square roots run
-        float4 nx[3];
-        if (lane < it.n4) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * lane);
-        }
-#pragma unroll 1
-        for (int i = lane; i < it.n4; i += 32) {
+        const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)it.b * p.obs_u.sb + base : nullptr;
+        const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)it.b * p.mask_u.sb + base : nullptr;
+        double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
+        auto body = [&](int i, const float4* mf, const float4* of, const unsigned* kk) {
             double mv[3][4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) widen4(nx[c], mv[c]);
-            if (i + 32 < it.n4) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * (i + 32));
-            }
+            for (int c = 0; c < 3; ++c) widen4(mf[c], mv[c]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const double n = sqrt((mv[0][j] * mv[0][j] + mv[1][j] * mv[1][j]) + mv[2][j] * mv[2][j]);
-                s_p += (1.0 - n) * (1.0 - n);
+                // |m| = s rsqrt(s): one reciprocal square root (1 ulp) instead of the IEEE square root's longer sequence
+                const double s2 = (mv[0][j] * mv[0][j] + mv[1][j] * mv[1][j]) + mv[2][j] * mv[2][j];
+                const double n = s2 > 0.0 ? s2 * rsqrt(s2) : 0.0;
+                double& acc = (j & 1) ? sp1 : sp0;
+                acc = fma(1.0 - n, 1.0 - n, acc);
             }
-            if (p.has_u) {
+            if (HAS_O) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float4 o = ldg4(po + c * p.obs_u.sc + 4 * i);
-                    const uchar4 k = ldg4(pm + c * p.mask_u.sc + 4 * i);
-                    const double d0 = u8_to_double(k.x) * (mv[c][0] - (double)o.x), d1 = u8_to_double(k.y) * (mv[c][1] - (double)o.y);
-                    const double d2 = u8_to_double(k.z) * (mv[c][2] - (double)o.z), d3 = u8_to_double(k.w) * (mv[c][3] - (double)o.w);
-                    s_u += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+                    // 0 / 1 masks: an unobserved pixel selects its own value as the observation (difference exactly 0)
+                    const unsigned k = kk[c];
+                    const double d0 = mv[c][0] - (double)sel_obs(k & 0xffu, of[c].x, mf[c].x), d1 = mv[c][1] - (double)sel_obs(k & 0xff00u, of[c].y, mf[c].y);
+                    const double d2 = mv[c][2] - (double)sel_obs(k & 0xff0000u, of[c].z, mf[c].z), d3 = mv[c][3] - (double)sel_obs(k & 0xff000000u, of[c].w, mf[c].w);
+                    su0 = fma(d0, d0, su0);
+                    su1 = fma(d1, d1, su1);
+                    su0 = fma(d2, d2, su0);
+                    su1 = fma(d3, d3, su1);
+                }
+            }
+        };
+        // PF elements of the magnetisation (the HBM stream) are prefetched into registers ahead of the one being processed;
+        // observations / masks (L2 hits: they broadcast over the batch and the batch index is innermost) load at the top.
+        float4 nx[PF > 0 ? PF : 1][3];
+#pragma unroll
+        for (int q = 0; q < PF; ++q)
+            if (lane + 32 * q < it.n4) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nx[q][c] = ldg4(m0 + c * p.x0.sc + 4 * (lane + 32 * q));
+            }
+#pragma unroll 1
+        for (int i0 = lane; i0 < it.n4; i0 += 32 * (PF > 0 ? PF : 1)) {
+#pragma unroll
+            for (int q = 0; q < (PF > 0 ? PF : 1); ++q) {
+                const int i = i0 + 32 * q;
+                if (i < it.n4) {
+                    float4 mf[3], of[3];
+                    unsigned kk[3];
+                    if (HAS_O) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            of[c] = ldg4(po + c * p.obs_u.sc + 4 * i);
+                            kk[c] = __ldg(reinterpret_cast<const unsigned*>(pm + c * p.mask_u.sc + 4 * i));
+                        }
+                    }
+                    if (PF > 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) mf[c] = nx[q][c];
+                        if (i + 32 * PF < it.n4) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) nx[q][c] = ldg4(m0 + c * p.x0.sc + 4 * (i + 32 * PF));
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) mf[c] = ldg4(m0 + c * p.x0.sc + 4 * i);
+                    }
+                    body(i, mf, of, kk);
                 }
             }
         }
-    }
-    if (p.has_a)
-        for (int item = warp0; item < g.n_a_items; item += nwarps) a_item_reduce(p, g, item, lane, s_a);
+        s_p += sp0 + sp1;
+        s_u += su0 + su1;
+    };
+    auto do_a = [&](int item) { a_item_reduce(p, g, item, lane, s_a); };
+    run_interleaved(warp0, nwarps, n_items, p.has_a ? g.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
     reduce_epilogue(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
-__global__ void __launch_bounds__(kThreads, 4)   // measured 8x6x2048^2: 0.547 / 0.458 / 0.400 ms at 2 / 3 / 4 CTAs per SM
+// three elements per lane in flight, two CTAs per SM (measured 8 x 6 x 2048^2: 0.322 ms; D = 2 at three CTAs 0.334, at four 0.364;
+// round 1's load-at-use form with sqrt + division 0.393)
+template <bool HAS_O>
+__global__ void __launch_bounds__(kThreads, 2)
 llg_norm_vjp_kernel(const __grid_constant__ Params p, const __grid_constant__ MarchGeom g, int n_items,
                     const double* __restrict__ scal, const double* __restrict__ upstream, float* __restrict__ g_x0,
                     float* __restrict__ g_dxdt) {
+    extern __shared__ __align__(16) unsigned char ring_mem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp0 = blockIdx.x * (kThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kThreads / 32);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(ring_mem);
     const double up = upstream ? __ldg(upstream) : 1.0;
     const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
     const int64_t plane = (int64_t)p.H * p.W;
-    for (int item = warp0; item < n_items; item += nwarps) {
+    auto do_u = [&](int item) {
         const NormItem it = norm_decode(p, g, item);
         const int base = p.ylo * p.W + 4 * it.first4;
         const float* m0 = reinterpret_cast<const float*>(p.x0.p) + (int64_t)it.b * p.x0.sb + (int64_t)p.ch_a * p.x0.sc + base;
-        const float* po = p.has_u ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)it.b * p.obs_u.sb + base : nullptr;
-        const unsigned char* pm = p.has_u ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)it.b * p.mask_u.sb + base : nullptr;
+        const float* po = HAS_O ? reinterpret_cast<const float*>(p.obs_u.p) + (int64_t)it.b * p.obs_u.sb + base : nullptr;
+        const unsigned char* pm = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)it.b * p.mask_u.sb + base : nullptr;
         float* gm = g_x0 + ((int64_t)it.b * p.C + p.ch_a) * plane + base;
         float* gd = g_dxdt ? g_dxdt + ((int64_t)it.b * p.C + p.ch_a) * plane + base : nullptr;
-        float4 nx[3];
-        if (lane < it.n4) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * lane);
-        }
-#pragma unroll 1
-        for (int i = lane; i < it.n4; i += 32) {
+        norm_item_stream<kNormD, HAS_O>(it.n4, lane, sbase, m0, p.x0.sc, po, p.obs_u.sc, pm, p.mask_u.sc,
+                                        [&](int i, const float4* mf, const float4* of, const unsigned* kk) {
             double mv[3][4], f[4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) widen4(nx[c], mv[c]);
-            if (i + 32 < it.n4) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) nx[c] = ldg4(m0 + c * p.x0.sc + 4 * (i + 32));
-            }
+            for (int c = 0; c < 3; ++c) widen4(mf[c], mv[c]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                // g_m = -c_p (1 - n) m / n  (0 where n == 0, as torch.linalg.norm's backward)
-                const double n = sqrt((mv[0][j] * mv[0][j] + mv[1][j] * mv[1][j]) + mv[2][j] * mv[2][j]);
-                f[j] = (n > 0.0) ? -c_p * (1.0 - n) / n : 0.0;
+                // g_m = -c_p (1 - n) m / n = c_p (1 - 1 / n) m  (0 where n == 0, as torch.linalg.norm's backward): one rsqrt, no division
+                const double s2 = (mv[0][j] * mv[0][j] + mv[1][j] * mv[1][j]) + mv[2][j] * mv[2][j];
+                f[j] = s2 > 0.0 ? fma(-c_p, rsqrt(s2), c_p) : 0.0;
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 double v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = f[j] * mv[c][j];
-                if (p.has_u) {
-                    const float4 o = ldg4(po + c * p.obs_u.sc + 4 * i);
-                    const uchar4 k = ldg4(pm + c * p.mask_u.sc + 4 * i);
-                    const double k0 = u8_to_double(k.x), k1 = u8_to_double(k.y), k2 = u8_to_double(k.z), k3 = u8_to_double(k.w);
-                    v[0] += c_u * (k0 * (k0 * (mv[c][0] - (double)o.x)));
-                    v[1] += c_u * (k1 * (k1 * (mv[c][1] - (double)o.y)));
-                    v[2] += c_u * (k2 * (k2 * (mv[c][2] - (double)o.z)));
-                    v[3] += c_u * (k3 * (k3 * (mv[c][3] - (double)o.w)));
+                if (HAS_O) {
+                    const unsigned k = kk[c];
+                    v[0] = fma(c_u, mv[c][0] - (double)sel_obs(k & 0xffu, of[c].x, mf[c].x), v[0]);
+                    v[1] = fma(c_u, mv[c][1] - (double)sel_obs(k & 0xff00u, of[c].y, mf[c].y), v[1]);
+                    v[2] = fma(c_u, mv[c][2] - (double)sel_obs(k & 0xff0000u, of[c].z, mf[c].z), v[2]);
+                    v[3] = fma(c_u, mv[c][3] - (double)sel_obs(k & 0xff000000u, of[c].w, mf[c].w), v[3]);
                 }
                 *reinterpret_cast<float4*>(gm + c * plane + 4 * i) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
                 if (gd) *reinterpret_cast<float4*>(gd + c * plane + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        }
-    }
-    for (int item = warp0; item < g.n_a_items; item += nwarps) a_item_vjp(p, g, item, lane, c_a, g_x0, g_dxdt);
+        });
+    };
+    auto do_a = [&](int item) { a_item_vjp_ring<3 * kNormD, kThreads, 2>(p, g, item, lane, sbase, c_a, g_x0, g_dxdt); };
+    run_interleaved(warp0, nwarps, n_items, g.n_a_items, (tid >> 5) & 1, do_u, do_a);
 }
