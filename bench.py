@@ -341,14 +341,13 @@ def run_ours(args):
                     "note": "bench-workload launch (8 MB fields, L2-resident, launch-latency regime: 12.6 MB is 1.9 us at peak); "
                             "the HBM-bound measurement of the same kernels is roofline_large_grid"}
 
-    # ---- the same kernels on grids far larger than L2 (config 5 shape; LLG 8 x 6 x 2048^2) -------------------
-    large = large_grid_rooflines(dev, peak) if rank == 0 and not args.skip_large else None
-
     # ---- end to end through the public API: host tensors in, host tensors out -------------------------------
     e2e, n_e2e = None, 0
     if not args.skip_e2e:
         est = ms_max / args.steps / 1e3
         n_e2e = args.e2e_steps or max(20, min(n_cfg, int(args.e2e_budget / max(est, 1e-6))))
+        # warm-up call, as the gpu_reference leg does for the reference (allocator blocks, cuDNN plans of the sample() path)
+        smp.sample(host["labels"], host["obs_a"], host["obs_u"], host["mask_a"], host["mask_u"], *z, return_losses=True, num_steps=3)
         barrier()
         t0 = time.perf_counter()
         # every rank samples ITS shard (the host tensors above are already per-rank), then the one collective of
@@ -396,6 +395,13 @@ def run_ours(args):
     gpu_ref = None
     if rank == 0 and world == 1 and not args.skip_gpu_ref and e2e is not None:
         gpu_ref = time_gpu_reference(args, net_cpu_state, prob, dev, B, n_e2e, host, z)
+
+    # ---- the same kernels on grids far larger than L2 (config 5 shape; LLG 8 x 6 x 2048^2) -------------------
+    # (after the end-to-end legs: its multi-GiB operands and empty_cache() calls hand the denoiser's activation blocks back to the
+    #  driver; the sample() calls timed above should see the allocator state the timed steps left)
+    gc.collect()
+    torch.cuda.empty_cache()
+    large = large_grid_rooflines(dev, peak) if rank == 0 and not args.skip_large else None
 
     net = net.cpu()
     del net
