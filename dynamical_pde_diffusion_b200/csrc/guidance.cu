@@ -23,6 +23,9 @@
 #include <atomic>
 #include <type_traits>
 
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 
 namespace dpde {
@@ -756,6 +759,7 @@ std::atomic<bool> g_fast_path{true};
 // [5] 1 = the LLG marching kernels send interior work items through their general loop too (A/B runs of the lean loop);
 // [6] 1 = the LLG m x H_eff residual runs the tile kernels on every size, 2 = the marching kernels on every size with W >= 128
 //     (default: marching on large grids, tiles on small ones)
+// [7] 1 = the LLG marching reduce pass feeds its lean items by cp.async instead of TMA
 std::atomic<int> g_tuning[8] = {};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -1042,12 +1046,57 @@ int llg_march_grid(K kernel, int64_t warp_items, int smem) {
     return clamp_grid((int64_t)sm_count() * occ, need, kMaxPartials);
 }
 
+// ---- TMA tensor maps for the lean interior items of the LLG marching kernels ---------------------------------
+// One map per tensor: dims (W, H, planes, batch) of fp32, box 68 columns x 1 row x 3 planes = one warp's row of the three
+// components (+ the four columns that align the box start to 16 bytes), 816 bytes per copy.  The encoder is a driver entry point (no link against libcuda).
+inline PFN_cuTensorMapEncodeTiled tma_encoder() {
+    static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    }();
+    return fn;
+}
+
+// planes = channels of the tensor, first_plane = channel the 3-plane box starts at (coordinate passed by the kernel)
+inline bool tma_map_f32(CUtensorMap* map, const View& v, int B, int planes, int H, int W) {
+    auto enc = tma_encoder();
+    if (!enc || !v.p || v.dtype != DPDE_F32 || W < 64 || planes < 3 || v.sc <= 0) return false;
+    if (!al(v.p, 16) || (W % 4) || (v.sc % 4) || (v.sb % 4)) return false;
+    const bool bcast = v.sb == 0;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)(bcast ? 1 : B)};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)v.sc * 4, (cuuint64_t)(bcast ? (int64_t)planes * v.sc : v.sb) * 4};
+    if (strides[2] == 0 || strides[2] % 16) return false;
+    cuuint32_t box[4] = {kLlgBoxCols, kLlgBoxRows, 3, 1}, estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(v.p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool HAS_D, bool HAS_O>
+bool llg_tma_maps(const Params& p, LlgTmaMaps* maps) {
+    bool ok = tma_map_f32(&maps->m, p.x0, p.B, p.C, p.H, p.W);
+    if (HAS_D) ok = ok && tma_map_f32(&maps->d, p.dxdt, p.B, p.C, p.H, p.W);
+    if (HAS_O) ok = ok && tma_map_f32(&maps->o, p.obs_u, p.B, 3, p.H, p.W);
+    maps->o_bcast = p.obs_u.sb == 0;
+    return ok;
+}
+
 template <bool HAS_D, bool HAS_O>
 int launch_llg_march_reduce(const Params& p, double* partials, unsigned int* ticket, double* sums, int finalize, double* scal, float* trace,
                             cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, false, true);
-    auto k = llg_march_reduce_kernel<HAS_D, HAS_O>;
-    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes()), kLlgThreads, llg_smem_bytes(), s>>>(p, g, partials, ticket, sums, finalize, scal, trace);
+    LlgTmaMaps none{};
+    // lean interior items fed by TMA (tuning key 7 = 1 switches it off: tests compare the two feeds bit for bit); falls back to the
+    // cp.async ring when a tensor map cannot be encoded (driver entry point missing, strides not multiples of 16 bytes)
+    if (g_tuning[7] != 1 && g.n_int_items > 0 && llg_tma_maps<HAS_D, HAS_O>(p, &none)) {
+        auto k = llg_march_reduce_kernel<HAS_D, HAS_O, true>;
+        const int smem = llg_tma_smem_bytes();
+        k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, smem), kLlgThreads, smem, s>>>(p, g, none, partials, ticket, sums, finalize, scal, trace);
+        return check_launch("dpde_guidance_reduce (llg march, tma)");
+    }
+    auto k = llg_march_reduce_kernel<HAS_D, HAS_O, false>;
+    k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes()), kLlgThreads, llg_smem_bytes(), s>>>(p, g, none, partials, ticket, sums, finalize, scal, trace);
     return check_launch("dpde_guidance_reduce (llg march)");
 }
 

@@ -40,6 +40,54 @@ constexpr int kLlgAD = 8;
 static_assert(kLlgAD * 32 * 36 == llg_warp_ring_bytes(), "a-plane ring must fit the warp's row ring exactly");
 __host__ __device__ constexpr int llg_smem_bytes() { return llg_ring_bytes(); }
 
+// ---- TMA feed of the lean interior items --------------------------------------------------------------------
+// One elected lane per warp issues one cp.async.bulk.tensor per field and ring element (box 64 columns x 1 row x 3 planes =
+// the warp's row of the three components, 768 bytes) instead of nine 8-byte cp.async per lane with their address
+// arithmetic; completion is counted on one mbarrier per ring slot of the warp.
+struct LlgTmaMaps {
+    CUtensorMap m, d, o;                     // x0, dxdt, obs_u
+    int o_bcast;                             // obs_u broadcasts over the batch (batch coordinate 0)
+};
+// The box start must be 16-byte aligned in the innermost dimension (measured: a box at column 58 faults, at 56 it loads), and a
+// strip starts at column 60 s - 2: the box is 68 columns wide and starts two columns earlier, at 60 s - 4; lane l reads its two
+// columns at byte 8 + 8 l of each 272-byte plane row.  Boxes sit on 128-byte boundaries (896 bytes apart).
+constexpr int kLlgBoxCols = 68, kLlgBoxRows = 2;                      // two rows per copy: half the issue / wait overhead per row
+constexpr int kLlgBoxRow = kLlgBoxCols * 4;                            // 272 bytes per plane row
+constexpr int kLlgBox = 3 * kLlgBoxRows * kLlgBoxRow;                  // 1632 bytes per copy, laid out [plane][row][68]
+constexpr int kLlgBoxPitch = 1664;                                     // boxes on 128-byte boundaries
+constexpr int kLlgTmaSlot = 3 * kLlgBoxPitch;                          // ring slot of a warp: m | dmdt | obs boxes of one row pair
+constexpr int kLlgTmaSlots = 2;
+__host__ __device__ constexpr int llg_tma_warp_bytes() { return kLlgTmaSlots * kLlgTmaSlot; }              // 9984
+__host__ __device__ constexpr int llg_tma_bar_bytes() { return (kLlgThreads / 32) * kLlgTmaSlots * 8; }
+__host__ __device__ constexpr int llg_tma_smem_bytes() { return (kLlgThreads / 32) * llg_tma_warp_bytes() + llg_tma_bar_bytes(); }
+
+__device__ __forceinline__ bool elect_one() {                        // one lane of the (converged) warp; ptxas then issues the TMA once, without a loop
+    unsigned pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// bounded spin: a barrier that never completes (a programming error) traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                 : "memory");
+}
+
 struct LlgMarchGeom {
     MarchGeom a;                             // a-plane streaming fields (a_plane4, a_block4, n_a_items, ...)
     int strips, R, chunks, n_items;          // u work item = (b innermost, strip, chunk)
@@ -321,29 +369,185 @@ __device__ __forceinline__ void llg_march_reduce_item(const Params& p, const Llg
     }
 }
 
+// TMA feed of one warp's two-slot ring.  row_m / row_d / row_o: grid row of box row 0 of pair 0 for the three fields (they differ
+// by the stencil offset: the magnetisation box holds the rows BELOW the two iterations of a pair).
+template <bool HAS_D, bool HAS_O>
+struct LlgTmaFeed {
+    const LlgTmaMaps* maps;
+    unsigned udata, bar0, data, lane;
+    int ub, ob, box_col, row_m, row_d, row_o, ch;
+
+    __device__ __forceinline__ void bind(const Params& p, const LlgLane& m, const LlgTmaMaps& mp, unsigned char* ring_mem, unsigned ring0, int wid,
+                                         int first_m, int first_d, int first_o) {
+        maps = &mp;
+        data = llg_warp_ring(ring_mem);
+        lane = threadIdx.x & 31;
+        // (the item decode divides: its results are broadcast once per item so that the compiler sees uniform values again)
+        ub = __shfl_sync(0xffffffffu, m.b, 0);
+        box_col = __shfl_sync(0xffffffffu, m.col0 - 2, 0);
+        const int ys = __shfl_sync(0xffffffffu, m.ys, 0);
+        row_m = ys + first_m;
+        row_d = ys + first_d;
+        row_o = ys + first_o;
+        ob = mp.o_bcast ? 0 : ub;
+        ch = p.ch_a;
+        udata = ring0 + wid * llg_tma_warp_bytes();
+        bar0 = ring0 + (kLlgThreads / 32) * llg_tma_warp_bytes() + wid * kLlgTmaSlots * 8;
+        // the previous item of this warp (cp.async ring of a general or an a-plane item, or TMA) has drained these bytes; order its
+        // generic-proxy accesses before the async-proxy writes that follow
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ void issue(int pair, int slot) const {
+        const int dr = __shfl_sync(0xffffffffu, 2 * pair, 0);         // one shuffle: the row coordinate reaches the TMA as a uniform value
+        if (elect_one()) {
+            const unsigned bar = bar0 + slot * 8, dst = udata + slot * kLlgTmaSlot;
+            mbar_expect_tx(bar, kLlgBox * (1 + (HAS_D ? 1 : 0) + (HAS_O ? 1 : 0)));
+            tma_load_4d(dst, &maps->m, box_col, row_m + dr, ch, ub, bar);
+            if (HAS_D) tma_load_4d(dst + kLlgBoxPitch, &maps->d, box_col, row_d + dr, ch, ub, bar);
+            if (HAS_O) tma_load_4d(dst + 2 * kLlgBoxPitch, &maps->o, box_col, row_o + dr, 0, ob, bar);
+        }
+    }
+    __device__ __forceinline__ void wait(int slot, unsigned& phases) const {
+        mbar_wait(bar0 + slot * 8, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+    }
+    __device__ __forceinline__ V6 get(int slot, int field, int r) const {
+        V6 o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 f = lds64f(data + slot * kLlgTmaSlot + field * kLlgBoxPitch + (c * kLlgBoxRows + r) * kLlgBoxRow + 8 + lane * 8);
+            o.v[c][0] = (double)f.x;
+            o.v[c][1] = (double)f.y;
+        }
+        return o;
+    }
+};
+
+// Lean interior item of the reduce pass with the ring fed by TMA.  Row pair P (rows 2P, 2P + 1 of the chunk) lives in ring slot
+// P & 1: the magnetisation box holds rows 2P + 1, 2P + 2 (the "row below" of the two iterations), the dmdt / obs boxes rows
+// 2P, 2P + 1.  Every pair is complete (R is even, the rows below the chunk are inside the grid), so there are no boundary flags.
+// `phases`: bit s = parity the next wait on slot s of this warp expects.
+// `wid` (warp index in the CTA) and the coordinates are values the compiler KNOWS to be warp-uniform (shuffle broadcasts) and the
+// issuing lane comes from elect.sync: then UTMALDG takes its operands from uniform registers directly; with per-lane values or
+// `lane == 0` ptxas wraps every copy in an ELECT / R2UR.BROADCAST loop (~10 instructions per copy).
+template <bool HAS_D, bool HAS_O>
+__device__ __forceinline__ void llg_march_reduce_item_tma(const Params& p, const LlgMarchGeom& g, const LlgLane& m, const LlgTmaMaps& maps,
+                                                          unsigned char* ring_mem, unsigned ring0, int wid, unsigned& phases, double& s_u,
+                                                          double& s_p) {
+    LlgRing<HAS_D, HAS_O> ring;                                       // pointers for the direct rows and the mask words
+    ring.bind(p, m, ring_mem);
+    const int W = p.W, n_it = g.R, n_pairs = n_it >> 1;
+    LlgK k;
+    k.h[0] = __ldg(p.coef + 3 * m.b);
+    k.h[1] = __ldg(p.coef + 3 * m.b + 1);
+    k.h[2] = __ldg(p.coef + 3 * m.b + 2);
+    k.kex = p.c_ex * p.inv_dx2;
+    k.g1 = p.tau * p.gamma;
+    k.g2 = p.tau * p.alpha;
+    LlgTmaFeed<HAS_D, HAS_O> feed;
+    feed.bind(p, m, maps, ring_mem, ring0, wid, 1, 0, 0);
+    feed.issue(0, 0);
+    feed.issue(1, 1);                                                 // n_it >= 4
+    auto off_of = [&](int e) -> int64_t { return (int64_t)(m.ys + e) * W; };
+    V6 mu = ring.direct_m(off_of(-1)), mc = ring.direct_m(off_of(0));
+    Mask3 mk = ring.masks(off_of(0));
+    double sp0 = 0.0, sp1 = 0.0, su0 = 0.0, su1 = 0.0;
+
+    auto row = [&](int it, auto J) {
+        constexpr int j = decltype(J)::value, slot = (j >> 1) & 1, r = j & 1;
+        if (r == 0) feed.wait(slot, phases);                          // the pair of rows it, it + 1
+        const V6 md = feed.get(slot, 0, r);
+        V6 dt{}, ob6{};
+        if (HAS_D) dt = feed.get(slot, 1, r);
+        if (HAS_O) ob6 = feed.get(slot, 2, r);
+        if (r == 1) {
+            __syncwarp();                                             // every lane has read the slot: it may be refilled
+            if ((it >> 1) + kLlgTmaSlots < n_pairs) feed.issue((it >> 1) + kLlgTmaSlots, slot);
+        }
+        const Mask3 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 1)) : Mask3{{0u, 0u, 0u}};
+        double lap[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double lf = __shfl_up_sync(0xffffffffu, mc.v[c][1], 1), rt = __shfl_down_sync(0xffffffffu, mc.v[c][0], 1);
+            lap2(mu.v[c], mc.v[c], md.v[c], lf, rt, lap[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double mm[3] = {mc.v[0][i], mc.v[1][i], mc.v[2][i]}, ll[3] = {lap[0][i], lap[1][i], lap[2][i]};
+            const double dd[3] = {dt.v[0][i], dt.v[1][i], dt.v[2][i]};
+            double H[3], a[3], rr[3];
+            llg_fwd_px(p, k, mm, ll, dd, H, a, rr);
+            double& acc = i ? sp1 : sp0;
+            acc = fma(rr[0], rr[0], acc);
+            acc = fma(rr[1], rr[1], acc);
+            acc = fma(rr[2], rr[2], acc);
+            if (HAS_O) {
+                double& au = i ? su1 : su0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double d = mm[c] - ob6.v[c][i];
+                    fma_where(au, d, d, mask_bit(mk, c, i));
+                }
+            }
+        }
+        mu = mc;
+        mc = md;
+        mk = mk_next;
+    };
+#pragma unroll 1
+    for (int gi = 0; gi < n_it / kLR; ++gi)                           // n_it = R is a multiple of the ring depth (4 rows = both slots)
+        static_for<kLR>([&](auto J) { row(gi * kLR + decltype(J)::value, J); });
+    // every issued pair has been waited for
+    if (m.out_ok) {
+        s_p += sp0 + sp1;
+        s_u += su0 + su1;
+    }
+}
+
 // four CTAs per SM (128 registers, a few spills outside the row loop): measured 0.386 ms against 0.403 ms at three CTAs / 168
 // registers and 0.551 ms at five / 96 (8 x 6 x 2048^2) -- the pass is latency-bound, occupancy pays until the spills reach the loop
-template <bool HAS_D, bool HAS_O>
+template <bool HAS_D, bool HAS_O, bool TMA>
 __global__ void __launch_bounds__(kLlgThreads, 4)
-llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, double* __restrict__ partials,
+llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, const __grid_constant__ LlgTmaMaps maps, double* __restrict__ partials,
                         unsigned int* __restrict__ ticket, double* __restrict__ sums, int finalize, double* __restrict__ scal,
                         float* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char ring_mem[];
+    extern __shared__ __align__(128) unsigned char ring_mem[];
     __shared__ double scratch[3 * (kLlgThreads / 32)];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int warp0 = blockIdx.x * (kLlgThreads / 32) + (tid >> 5), nwarps = gridDim.x * (kLlgThreads / 32);
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp index as a value the compiler knows to be warp-uniform
+    const int warp0 = blockIdx.x * (kLlgThreads / 32) + wid, nwarps = gridDim.x * (kLlgThreads / 32);
     double s_a = 0.0, s_u = 0.0, s_p = 0.0;
+    unsigned phases = 0u;                                             // TMA: parity expected by the next wait on each ring slot of this warp
+    // TMA: a warp's ring region is llg_tma_warp_bytes() long; `ring` is biased so that llg_warp_ring(ring) lands on it
+    unsigned char* ring = TMA ? ring_mem + (tid >> 5) * (llg_tma_warp_bytes() - llg_warp_ring_bytes()) : ring_mem;
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring_mem);
+    const unsigned bar0 = ring0 + (kLlgThreads / 32) * llg_tma_warp_bytes() + wid * kLlgTmaSlots * 8;
+    if (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kLlgTmaSlots; ++s) mbar_init(bar0 + s * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
     // a-plane items in the LDG form (eight loads per lane in flight): streamed through the warp's ring bytes this pass ran
     // 0.377 ms instead of 0.352 ms (8 x 6 x 2048^2) -- every reduce pass measured prefers LDG, every VJP pass the ring
     auto do_a = [&](int item) { a_item_reduce(p, g.a, item, lane, s_a); };
     auto do_u = [&](int item) {
         bool interior;
         const LlgLane m = llg_lane_decode(p, g, item, lane, interior);
-        if (interior)                                                  // warp-uniform: one strip per warp
-            llg_march_reduce_item<HAS_D, HAS_O, true>(p, g, m, ring_mem, s_u, s_p);
-        else
-            llg_march_reduce_item<HAS_D, HAS_O, false>(p, g, m, ring_mem, s_u, s_p);
+        if (TMA) interior = __shfl_sync(0xffffffffu, (int)interior, 0) != 0;   // uniform by construction; now the compiler knows it too
+        if (interior) {                                                // warp-uniform: one strip per warp
+            if (TMA)
+                llg_march_reduce_item_tma<HAS_D, HAS_O>(p, g, m, maps, ring, ring0, wid, phases, s_u, s_p);
+            else
+                llg_march_reduce_item<HAS_D, HAS_O, true>(p, g, m, ring, s_u, s_p);
+        } else {
+            llg_march_reduce_item<HAS_D, HAS_O, false>(p, g, m, ring, s_u, s_p);
+        }
     };
     run_interleaved(warp0, nwarps, g.n_items, p.has_a ? g.a.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
     reduce_epilogue_n<kLlgThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
@@ -355,6 +559,8 @@ llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant_
 // g2 = G_H[jo-1], g1 = G_H[jo], g0 = G_H[jo+1], the pointwise part kept from the previous iteration and the observation
 // term at m[jo] = mu.  Ring element s is row ys - 2 + s: md = element it+2, dmdt[j] = element it+1, obs[jo] = element it.
 // ---------------------------------------------------------------------------------------------------------
+// (The TMA feed of the reduce pass was tried here too -- same results bit for bit, 0.687 ms against 0.688 ms: at eight warps per SM this
+//  pass is not limited by the load/store unit, so it keeps the cp.async ring.)
 template <bool HAS_D, bool HAS_O, bool LEAN>
 __device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMarchGeom& g, const LlgLane& m, unsigned char* ring_mem, double c_u,
                                                    double c_p, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {

@@ -106,6 +106,14 @@ def test_llg_residual_full_size_against_the_torch_oracle_on_device(K0):
     gx, gd = eng.seed(x0, dxdt, w, want_dxdt_grad=True)
     gx2, _ = eng.seed(x0, dxdt, w)                       # without d / d dmdt the VJP takes its lean interior loop
     assert torch.equal(gx, gx2)
+    from dynamical_pde_diffusion_b200 import _ffi
+    s_tma = eng.scalars[:4].clone()
+    try:                                                 # reduce pass fed by cp.async instead of TMA: same bits
+        _ffi.check(_ffi.lib().dpde_set_tuning(7, 1))
+        eng.reduce(x0, dxdt, w)
+        assert torch.equal(eng.scalars[:4], s_tma)
+    finally:
+        _ffi.check(_ffi.lib().dpde_set_tuning(7, 0))
     losses, gx_ref, gd_ref = _torch_guidance(x0, dxdt, obs_a, obs_u, mask_a, mask_u, ch_a,
                                              lambda mm, dm: R.llg_residual_loss(mm, dm, field, dx, rc), w)
     got = eng.scalars[:3].cpu().tolist()

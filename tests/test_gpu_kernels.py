@@ -317,7 +317,8 @@ def test_llg_residual_marching_kernels(shape, rows, want_d):
     """The row-marching LLG kernels (llg_march.cuh; default on large grids only) forced onto small grids by tuning key 6 = 2:
     against the closed form, with chunk lengths that give the reduce pass (8) resp. the VJP (6, 14: R + 2 a multiple of the
     ring depth) interior work items for the lean loop, with and without the d / d dmdt output (which disables the lean VJP
-    loop), with K0 != 0, and against the tile kernels (key 6 = 1) and the general loop only (key 5 = 1)."""
+    loop), with K0 != 0, and against the tile kernels (key 6 = 1), the general loop only (key 5 = 1) and the cp.async feed of the
+    reduce pass instead of TMA (key 7 = 1: bit-identical)."""
     from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants, _ffi
     from dynamical_pde_diffusion_b200._ffi import PDE_LLG_RESIDUAL
 
@@ -345,7 +346,10 @@ def test_llg_residual_marching_kernels(shape, rows, want_d):
     try:
         _ffi.check(T(2, rows))
         _ffi.check(T(6, 2))
-        s_m, g_m, gd_m = run()                    # marching, lean loop where the geometry allows it
+        s_m, g_m, gd_m = run()                    # marching, lean loop where the geometry allows it (reduce pass: TMA-fed ring)
+        _ffi.check(T(7, 1))
+        s_c, g_c, gd_c = run()                    # the same with the cp.async feed in the reduce pass
+        _ffi.check(T(7, 0))
         _ffi.check(T(5, 1))
         s_g, g_g, gd_g = run()                    # marching, general loop only
         _ffi.check(T(5, 0))
@@ -353,8 +357,9 @@ def test_llg_residual_marching_kernels(shape, rows, want_d):
         _ffi.check(T(2, 0))
         s_t, g_t, gd_t = run()                    # convert-once tiles
     finally:
-        for k in (2, 5, 6):
+        for k in (2, 5, 6, 7):
             _ffi.check(T(k, 0))
+    assert torch.equal(s_c, s_m) and torch.equal(g_c, g_m), "TMA-fed and cp.async-fed reduce passes differ"
     loss, gm_ref, gd_ref = R.llg_residual_guidance_numpy(x0[:, ch_a:].double().numpy(), dxdt[:, ch_a:].double().numpy(),
                                                          field.numpy(), dx, rc, w_pde=w[2])
     mu = np.broadcast_to(mask_u.double().numpy(), (B, 3, H, W))
