@@ -759,7 +759,7 @@ std::atomic<bool> g_fast_path{true};
 // [5] 1 = the LLG marching kernels send interior work items through their general loop too (A/B runs of the lean loop);
 // [6] 1 = the LLG m x H_eff residual runs the tile kernels on every size, 2 = the marching kernels on every size with W >= 128
 //     (default: marching on large grids, tiles on small ones)
-// [7] 1 = the LLG marching reduce pass feeds its lean items by cp.async instead of TMA
+// [7] 1 = the LLG marching kernels without TMA: reduce pass with the cp.async feed, VJP as the two-CTA kernel with register windows
 std::atomic<int> g_tuning[8] = {};
 
 inline bool al(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -1073,6 +1073,26 @@ inline bool tma_map_f32(CUtensorMap* map, const View& v, int B, int planes, int 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// One zeroed work-queue counter for a launch on stream `s`: a slot of a small device array, cleared by a stream-ordered memset.  Slots are
+// handed out round-robin; a slot is reused after kQueueSlots further launches of this process.
+constexpr int kQueueSlots = 256;
+__device__ unsigned int g_queue_slots[kQueueSlots];
+inline unsigned int* work_queue_counter(cudaStream_t s) {
+    static std::atomic<unsigned> next{0};
+    static thread_local unsigned int* base[16] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned int*& b = base[dev & 15];
+    if (!b || dev > 15) {
+        void* ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_queue_slots) != cudaSuccess) return nullptr;
+        b = reinterpret_cast<unsigned int*>(ptr);
+    }
+    unsigned int* slot = b + (next.fetch_add(1) % kQueueSlots);
+    if (cudaMemsetAsync(slot, 0, sizeof(unsigned int), s) != cudaSuccess) return nullptr;
+    return slot;
+}
+
 template <bool HAS_D, bool HAS_O>
 bool llg_tma_maps(const Params& p, LlgTmaMaps* maps) {
     bool ok = tma_map_f32(&maps->m, p.x0, p.B, p.C, p.H, p.W);
@@ -1104,6 +1124,17 @@ template <bool HAS_D, bool HAS_O>
 int launch_llg_march_vjp(const Params& p, const double* scal, const double* upstream, float* g_x0, float* g_dxdt, cudaStream_t s) {
     const LlgMarchGeom g = llg_march_geometry(p, true, g_dxdt == nullptr);
     auto k = llg_march_vjp_kernel<HAS_D, HAS_O>;
+    LlgTmaMaps maps{};
+    // three CTAs per SM: TMA-fed lean items without register windows + light general items, dynamic longest-first queue (llg_vjp_lean3_kernel);
+    // tuning key 7 = 1 keeps the two-CTA kernel with the cp.async ring (tests compare the two bit for bit), which is also the fallback when
+    // d / d dmdt is wanted (no interior rectangle) or a tensor map cannot be encoded
+    if (g_tuning[7] != 1 && g.n_int_items > 0 && (g.R + 2) >= 8 && llg_tma_maps<HAS_D, HAS_O>(p, &maps)) {
+        auto k3 = llg_vjp_lean3_kernel<HAS_D, HAS_O>;
+        unsigned int* queue = work_queue_counter(s);
+        if (!queue) return fail(DPDE_ERR_CUDA, "dpde_guidance_vjp: work-queue counter unavailable");
+        k3<<<llg_march_grid(k3, (int64_t)g.n_items + g.a.n_a_items, llg_v3_smem_bytes()), kLlgThreads, llg_v3_smem_bytes(), s>>>(p, g, maps, scal, upstream, g_x0, g_dxdt, queue);
+        return check_launch("dpde_guidance_vjp (llg march, three CTAs)");
+    }
     k<<<llg_march_grid(k, (int64_t)g.n_items + g.a.n_a_items, llg_smem_bytes()), kLlgThreads, llg_smem_bytes(), s>>>(p, g, scal, upstream, g_x0, g_dxdt);
     return check_launch("dpde_guidance_vjp (llg march)");
 }

@@ -684,6 +684,357 @@ __device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMar
     cp_async_wait<0>();
 }
 
+// =========================================================================================================
+// VJP at THREE CTAs per SM (the default on large grids; llg_march_vjp_kernel above is the fallback).  168 registers instead of 252:
+//   * no register windows of m: the lean items keep rows y - 1, y, y + 1 in shared memory -- three two-row TMA boxes per field (pairs
+//     Q, Q + 1 resident, Q + 2 in flight) -- and a lane reads its columns AND its horizontal neighbours from the 68-column box (no
+//     shuffles for m); the general items read the same rows back from their four-deep cp.async ring;
+//   * scatter form of the transposed stencil: only G_H[y-1] and the partial gradient P[y-1] live across iterations;
+//   * TMA feed of the lean items: no per-lane load addresses;
+//   * a dynamic work queue, longest items first (below).
+// Measured on 8 x 6 x 2048^2: 0.688 -> 0.586 ms, output bit-identical to the two-CTA kernel.  Steps: lean items alone in this form 0.471 ms
+// (+ a separate launch of the general items 0.245 ms: one 66-row edge item per warp, nothing to overlap with); general items in the same
+// kernel with the static round-robin 0.684 ms (the last chunk's edge items come last and take 245 us each); with the queue 0.586 ms.
+// =========================================================================================================
+constexpr int kLlgV3Slots = 3;
+__host__ __device__ constexpr int llg_v3_warp_bytes() { return kLlgV3Slots * 3 * kLlgBoxPitch; }                     // 14976
+__host__ __device__ constexpr int llg_v3_smem_bytes() { return (kLlgThreads / 32) * (llg_v3_warp_bytes() + kLlgV3Slots * 8); }
+
+// interior item index -> lane geometry (batch innermost, then strip, then chunk, inside the interior rectangle)
+__device__ __forceinline__ LlgLane llg_lane_interior(const Params& p, const LlgMarchGeom& g, int idx, int lane) {
+    LlgLane m;
+    const unsigned ns = (unsigned)(g.s_hi - g.s_lo + 1), t = (unsigned)idx / (unsigned)p.B;
+    m.b = (int)((unsigned)idx - t * p.B);
+    const unsigned cq = t / ns;
+    const int strip = g.s_lo + (int)(t - cq * ns), chunk = g.c_lo + (int)cq;
+    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
+    m.lane_ok = true;
+    m.out_ok = lane >= 1 && lane <= 30;
+    m.colc = m.col0;
+    m.left_edge = m.right_edge = false;
+    m.ys = p.ylo + chunk * g.R;
+    m.ye = m.ys + g.R;
+    return m;
+}
+
+template <bool HAS_D, bool HAS_O>
+__device__ __forceinline__ void llg_vjp_lean3_item(const Params& p, const LlgMarchGeom& g, const LlgLane& m, const LlgTmaMaps& maps, unsigned ring0,
+                                                   int wid, unsigned& phases, double c_u, double c_p, float* __restrict__ g_x0) {
+    const unsigned lane = threadIdx.x & 31;
+    const int W = p.W, n_it = g.R + 2, n_half = n_it >> 1, n_pairs = n_half + 1;
+    const int64_t plane = (int64_t)p.H * W;
+    // uniform coordinates (broadcast: the compiler then keeps them in uniform registers)
+    const int ub = __shfl_sync(0xffffffffu, m.b, 0), box_col = __shfl_sync(0xffffffffu, m.col0 - 2, 0), r0 = __shfl_sync(0xffffffffu, m.ys - 2, 0);
+    const int ob = maps.o_bcast ? 0 : ub;
+    const unsigned udata = ring0 + wid * llg_v3_warp_bytes(), bar0 = ring0 + (kLlgThreads / 32) * llg_v3_warp_bytes() + wid * kLlgV3Slots * 8;
+    const unsigned own = udata + 8 + lane * 8;                        // the lane's two columns inside a box row
+    auto issue = [&](int q, unsigned slot) {                          // pair q = rows r0 + 2q, r0 + 2q + 1 of all three fields
+        const int row = __shfl_sync(0xffffffffu, r0 + 2 * q, 0);
+        const unsigned us = __shfl_sync(0xffffffffu, slot, 0);
+        if (elect_one()) {
+            const unsigned bar = bar0 + us * 8, dst = udata + us * (3 * kLlgBoxPitch);
+            mbar_expect_tx(bar, kLlgBox * (1 + (HAS_D ? 1 : 0) + (HAS_O ? 1 : 0)));
+            tma_load_4d(dst, &maps.m, box_col, row, p.ch_a, ub, bar);
+            if (HAS_D) tma_load_4d(dst + kLlgBoxPitch, &maps.d, box_col, row, p.ch_a, ub, bar);
+            if (HAS_O) tma_load_4d(dst + 2 * kLlgBoxPitch, &maps.o, box_col, row, 0, ob, bar);
+        }
+    };
+    auto wait = [&](unsigned slot) {
+        mbar_wait(bar0 + slot * 8, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+    };
+    auto at = [&](unsigned slot, int field, int c, int r) { return own + slot * (3 * kLlgBoxPitch) + field * kLlgBoxPitch + (c * kLlgBoxRows + r) * kLlgBoxRow; };
+    auto get = [&](unsigned slot, int field, int r) {
+        V6 o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 f = lds64f(at(slot, field, c, r));
+            o.v[c][0] = (double)f.x;
+            o.v[c][1] = (double)f.y;
+        }
+        return o;
+    };
+    LlgK k;
+    k.h[0] = __ldg(p.coef + 3 * m.b);
+    k.h[1] = __ldg(p.coef + 3 * m.b + 1);
+    k.h[2] = __ldg(p.coef + 3 * m.b + 2);
+    k.kex = p.c_ex * p.inv_dx2;
+    k.g1 = p.tau * p.gamma;
+    k.g2 = p.tau * p.alpha;
+    const double cl = -c_p * p.tau, ck = cl * k.kex;
+    float* gm = g_x0 + ((int64_t)m.b * p.C + p.ch_a) * plane + m.colc;
+    const unsigned char* pk = HAS_O ? reinterpret_cast<const unsigned char*>(p.mask_u.p) + (int64_t)m.b * p.mask_u.sb + m.colc : nullptr;
+    auto masks = [&](int row) {
+        Mask3 o{{0u, 0u, 0u}};
+        if (HAS_O) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o.k[c] = __ldg(reinterpret_cast<const unsigned short*>(pk + (int64_t)c * p.mask_u.sc + (int64_t)row * W));
+        }
+        return o;
+    };
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();                                                     // the previous item of this warp has drained the ring
+    issue(0, 0);
+    issue(1, 1);
+    issue(2, 2);                                                      // n_pairs >= 5
+    V6 gp{}, P{};
+    Mask3 mk = masks(m.ys - 1);                                       // masks of the row evaluated in THIS iteration
+    wait(0);
+    unsigned sa = 0, sb = 1;                                          // slots of pairs q, q + 1
+
+    // one iteration: rows y - 1, y, y + 1 at (slot, box row) su/ru, sc/rc, sd/rd; y = r0 + it + 1
+    auto row = [&](int it, unsigned su, int ru, unsigned sc_, int rc, unsigned sd, int rd) {
+        const int y = r0 + it + 1;
+        const Mask3 mk_next = (HAS_O && it + 1 < n_it) ? masks(y + 1) : Mask3{{0u, 0u, 0u}};
+        double lap[3][2];
+        V6 mc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned ac = at(sc_, 0, c, rc);
+            const float2 fc = lds64f(ac), fu = lds64f(at(su, 0, c, ru)), fd = lds64f(at(sd, 0, c, rd));
+            const float fl = __uint_as_float(lds32(ac - 4)), fr = __uint_as_float(lds32(ac + 8));
+            mc.v[c][0] = (double)fc.x;
+            mc.v[c][1] = (double)fc.y;
+            const double up[2] = {(double)fu.x, (double)fu.y}, dn[2] = {(double)fd.x, (double)fd.y};
+            lap2(up, mc.v[c], dn, (double)fl, (double)fr, lap[c]);
+        }
+        V6 dt{}, ob6{};
+        if (HAS_D) dt = get(sc_, 1, rc);
+        if (HAS_O) ob6 = get(sc_, 2, rc);
+        V6 g0, ln;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double mm[3] = {mc.v[0][i], mc.v[1][i], mc.v[2][i]}, ll[3] = {lap[0][i], lap[1][i], lap[2][i]};
+            const double dd[3] = {dt.v[0][i], dt.v[1][i], dt.v[2][i]};
+            double H[3], a[3], rr[3], GH[3], Gm[3];
+            llg_fwd_px(p, k, mm, ll, dd, H, a, rr);
+            llg_bwd_px(p, mm, H, a, rr, GH, Gm);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                g0.v[c][i] = GH[c];
+                ln.v[c][i] = Gm[c];
+            }
+        }
+        const bool emit = it >= 2 && m.out_ok;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double o0 = fma(ck, g0.v[c][0], P.v[c][0]), o1 = fma(ck, g0.v[c][1], P.v[c][1]);
+            if (emit) *reinterpret_cast<float2*>(gm + c * plane + (int64_t)(y - 1) * W) = make_float2((float)o0, (float)o1);
+            const double l = __shfl_up_sync(0xffffffffu, g0.v[c][1], 1), q = __shfl_down_sync(0xffffffffu, g0.v[c][0], 1);
+            const double a0 = (gp.v[c][0] + (l + g0.v[c][1])) - 4.0 * g0.v[c][0];
+            const double a1 = (gp.v[c][1] + (g0.v[c][0] + q)) - 4.0 * g0.v[c][1];
+            double v0 = fma(ck, a0, cl * ln.v[c][0]), v1 = fma(ck, a1, cl * ln.v[c][1]);
+            if (HAS_O) {
+                fma_where(v0, c_u, mc.v[c][0] - ob6.v[c][0], mask_bit(mk, c, 0));
+                fma_where(v1, c_u, mc.v[c][1] - ob6.v[c][1], mask_bit(mk, c, 1));
+            }
+            P.v[c][0] = v0;
+            P.v[c][1] = v1;
+        }
+        gp = g0;
+        mk = mk_next;
+    };
+#pragma unroll 1
+    for (int q = 0; q < n_half; ++q) {
+        wait(sb);                                                     // pair q + 1
+        row(2 * q, sa, 0, sa, 1, sb, 0);                              // y - 1, y in pair q; y + 1 opens pair q + 1
+        row(2 * q + 1, sa, 1, sb, 0, sb, 1);
+        __syncwarp();                                                 // every lane is done with pair q: its slot may be refilled
+        if (q + kLlgV3Slots < n_pairs) issue(q + kLlgV3Slots, sa);
+        sa = sb;
+        sb = sb == kLlgV3Slots - 1 ? 0u : sb + 1;
+    }
+}
+
+// General (edge) item of the same kernel: cp.async ring of the lane's own columns (reflected rows by the loader), the three
+// magnetisation rows y - 1, y, y + 1 read back from the four-deep ring (no register windows; the horizontal neighbours are the
+// adjacent lanes' ring bytes, visible after a __syncwarp), scatter form with the edge weights of the transposed stencil.
+// Ring element s = row ys - 2 + s: iteration `it` (row y = ys - 1 + it) reads m of elements it, it + 1, it + 2 and dmdt / obs of it + 1.
+template <bool HAS_D, bool HAS_O>
+__device__ __forceinline__ void llg_vjp_general3_item(const Params& p, const LlgMarchGeom& g, const LlgLane& m, unsigned char* ring_mem, double c_u,
+                                                      double c_p, float* __restrict__ g_x0, float* __restrict__ g_dxdt) {
+    LlgRing<HAS_D, HAS_O> ring;
+    ring.bind(p, m, ring_mem);
+    const int W = p.W, rows = m.ye - m.ys, n_it = rows + 2;
+    const int64_t plane = (int64_t)p.H * W;
+    LlgK k;
+    k.h[0] = __ldg(p.coef + 3 * m.b);
+    k.h[1] = __ldg(p.coef + 3 * m.b + 1);
+    k.h[2] = __ldg(p.coef + 3 * m.b + 2);
+    k.kex = p.c_ex * p.inv_dx2;
+    k.g1 = p.tau * p.gamma;
+    k.g2 = p.tau * p.alpha;
+    const double cl = -c_p * p.tau, ck = cl * k.kex;
+    float* gm = g_x0 + ((int64_t)m.b * p.C + p.ch_a) * plane + m.colc;
+    float* gd = g_dxdt ? g_dxdt + ((int64_t)m.b * p.C + p.ch_a) * plane + m.colc : nullptr;
+    auto off_of = [&](int e) -> int64_t { return (int64_t)row_offset(p, m.ys - 2 + e); };
+    // consumed: m for s in [0, n_it + 2), dmdt for s in [1, n_it + 1), obs for s in [2, n_it)
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kLR; ++s) ring.issue(s, off_of(s), s < n_it + 2, s >= 1 && s < n_it + 1, s >= 2 && s < n_it);
+    V6 gp{}, P{};
+    Mask3 mk = ring.masks(off_of(1));
+    const double wl0 = m.left_edge ? 0.0 : (m.col0 - 1 == 0 ? 2.0 : 1.0), wl1 = m.col0 == 0 ? 2.0 : 1.0;
+    const double wr0 = m.col0 + 1 == p.W - 1 ? 2.0 : 1.0, wr1 = m.right_edge ? 0.0 : (m.col0 + 2 == p.W - 1 ? 2.0 : 1.0);
+
+    auto row = [&](int it, auto J, bool refill_m, bool refill_d, bool refill_o) {
+        constexpr int j = decltype(J)::value;
+        cp_async_wait<kLR - 3>();                                     // own copies of elements <= it + 2 have landed ...
+        __syncwarp();                                                 // ... and so have the neighbours'
+        const int y = m.ys - 1 + it;
+        double lap[3][2];
+        V6 mc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned ac = ring.base + llg_slot(c, j + 1);
+            const float2 fc = lds64f(ac), fu = lds64f(ring.base + llg_slot(c, j)), fd = lds64f(ring.base + llg_slot(c, j + 2));
+            float fl = __uint_as_float(lds32(ac - 4)), fr = __uint_as_float(lds32(ac + 8));
+            if (m.left_edge) fl = fc.y;                               // reflect: m[-1] = m[1]
+            if (m.right_edge) fr = fc.x;
+            mc.v[c][0] = (double)fc.x;
+            mc.v[c][1] = (double)fc.y;
+            const double up[2] = {(double)fu.x, (double)fu.y}, dn[2] = {(double)fd.x, (double)fd.y};
+            lap2(up, mc.v[c], dn, (double)fl, (double)fr, lap[c]);
+        }
+        const V6 dt = ring.get_f(3, j + 1, HAS_D), ob = ring.get_f(6, j + 1, HAS_O);
+        __syncwarp();                                                 // every lane has read slot j (also as a neighbour): refill it
+        ring.issue(j, off_of(it + kLR), refill_m, refill_d, refill_o);
+        const Mask3 mk_next = (HAS_O && it + 1 < n_it) ? ring.masks(off_of(it + 2)) : Mask3{{0u, 0u, 0u}};
+        // the residual exists for rows ylo-1 .. yhi that lie inside the global grid; elsewhere G_H and G_m are zero
+        const bool need = y >= p.ylo - 1 && y <= p.yhi && y + p.yg0 >= 0 && y + p.yg0 < p.Hg && m.lane_ok;
+        V6 g0, ln;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double mm[3] = {mc.v[0][i], mc.v[1][i], mc.v[2][i]}, ll[3] = {lap[0][i], lap[1][i], lap[2][i]};
+            const double dd[3] = {dt.v[0][i], dt.v[1][i], dt.v[2][i]};
+            double H[3], a[3], rr[3], GH[3], Gm[3];
+            llg_fwd_px(p, k, mm, ll, dd, H, a, rr);
+            llg_bwd_px(p, mm, H, a, rr, GH, Gm);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                g0.v[c][i] = need ? GH[c] : 0.0;
+                ln.v[c][i] = need ? Gm[c] : 0.0;
+            }
+            if (gd && it >= 1 && y < m.ye && m.out_ok) {              // d loss / d dmdt = c_p r (row y is an owned row)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gd[c * plane + (int64_t)y * W + i] = (float)(c_p * rr[c]);
+            }
+        }
+        const bool emit = it >= 2 && y - 1 < m.ye && m.out_ok;
+        const int gy = y + p.yg0;                                     // global row of y; the row completed now is gy - 1
+        const double wu = gy == 0 ? 0.0 : (gy == 1 ? 2.0 : 1.0);
+        const double ckd = ck * (gy - 1 == p.Hg - 1 ? 0.0 : (gy - 1 == p.Hg - 2 ? 2.0 : 1.0));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double o0 = fma(ckd, g0.v[c][0], P.v[c][0]), o1 = fma(ckd, g0.v[c][1], P.v[c][1]);
+            if (emit) *reinterpret_cast<float2*>(gm + c * plane + (int64_t)(y - 1) * W) = make_float2((float)o0, (float)o1);
+            const double l = __shfl_up_sync(0xffffffffu, g0.v[c][1], 1), q = __shfl_down_sync(0xffffffffu, g0.v[c][0], 1);
+            const double a0 = (wu * gp.v[c][0] + (wl0 * l + wr0 * g0.v[c][1])) - 4.0 * g0.v[c][0];
+            const double a1 = (wu * gp.v[c][1] + (wl1 * g0.v[c][0] + wr1 * q)) - 4.0 * g0.v[c][1];
+            double v0 = fma(ck, a0, cl * ln.v[c][0]), v1 = fma(ck, a1, cl * ln.v[c][1]);
+            if (HAS_O) {
+                fma_where(v0, c_u, mc.v[c][0] - ob.v[c][0], mask_bit(mk, c, 0));
+                fma_where(v1, c_u, mc.v[c][1] - ob.v[c][1], mask_bit(mk, c, 1));
+            }
+            P.v[c][0] = v0;
+            P.v[c][1] = v1;
+        }
+        gp = g0;
+        mk = mk_next;
+    };
+    const int groups = (n_it + kLR - 1) / kLR;
+#pragma unroll 1
+    for (int gi = 0; gi < groups; ++gi)
+        static_for<kLR>([&](auto J) {
+            const int it = gi * kLR + decltype(J)::value, sn = it + kLR;
+            row(it, J, sn < n_it + 2, sn < n_it + 1, sn < n_it);
+        });
+    cp_async_wait<0>();
+}
+
+// general (edge) item index -> (strip, chunk, b): first the boundary chunks of every strip, then the edge strips of the interior chunks
+__device__ __forceinline__ LlgLane llg_lane_general(const Params& p, const LlgMarchGeom& g, int idx, int lane) {
+    const int nc = g.c_hi - g.c_lo + 1, ns = g.s_hi - g.s_lo + 1;
+    const int n_boundary = (g.chunks - nc) * g.strips * p.B;
+    int strip, chunk;
+    const unsigned t = (unsigned)(idx < n_boundary ? idx : idx - n_boundary) / (unsigned)p.B;
+    const int b = (int)((unsigned)(idx < n_boundary ? idx : idx - n_boundary) - t * p.B);
+    if (idx < n_boundary) {
+        const int cq = (int)(t / (unsigned)g.strips);
+        strip = (int)(t - (unsigned)cq * g.strips);
+        chunk = cq < g.c_lo ? cq : g.c_hi + 1 + (cq - g.c_lo);
+    } else {
+        const int es = g.strips - ns, cq = (int)(t / (unsigned)es), e = (int)(t - (unsigned)cq * es);
+        chunk = g.c_lo + cq;
+        strip = e < g.s_lo ? e : g.s_hi + 1 + (e - g.s_lo);
+    }
+    LlgLane m;
+    m.b = b;
+    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
+    m.lane_ok = m.col0 >= 0 && m.col0 < p.W;
+    m.out_ok = m.lane_ok && lane >= 1 && lane <= 30;
+    m.colc = m.lane_ok ? m.col0 : 0;
+    m.left_edge = m.col0 == 0;
+    m.right_edge = m.col0 + 2 == p.W;
+    m.ys = p.ylo + chunk * g.R;
+    m.ye = min(m.ys + g.R, p.yhi);
+    return m;
+}
+
+// Work queue (one atomic counter per launch): the slow general items first, then the lean items with the a-plane items mixed in evenly --
+// longest first, fetched dynamically, so that no warp is left with a 245-us edge item when the others have finished (with the static
+// round-robin of the other kernels the last chunk's edge items came last and the kernel was no faster than at two CTAs per SM).
+template <bool HAS_D, bool HAS_O>
+__global__ void __launch_bounds__(kLlgThreads, 3)
+llg_vjp_lean3_kernel(const __grid_constant__ Params p, const __grid_constant__ LlgMarchGeom g, const __grid_constant__ LlgTmaMaps maps,
+                     const double* __restrict__ scal, const double* __restrict__ upstream, float* __restrict__ g_x0, float* __restrict__ g_dxdt,
+                     unsigned int* __restrict__ queue) {
+    extern __shared__ __align__(128) unsigned char ring_mem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const double up = upstream ? __ldg(upstream) : 1.0;
+    const double c_a = __ldg(scal + 4) * up, c_u = __ldg(scal + 5) * up, c_p = __ldg(scal + 6) * up;
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring_mem);
+    unsigned phases = 0u;
+    {
+        const unsigned bar0 = ring0 + (kLlgThreads / 32) * llg_v3_warp_bytes() + wid * kLlgV3Slots * 8;
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kLlgV3Slots; ++s) mbar_init(bar0 + s * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    auto do_a = [&](int item) {
+        __syncwarp();
+        a_item_vjp_ring<kLlgAD, 32, 2>(p, g.a, item, lane, ring0 + wid * llg_v3_warp_bytes(), c_a, g_x0, g_dxdt);
+        __syncwarp();
+    };
+    unsigned char* ring = ring_mem + (tid >> 5) * (llg_v3_warp_bytes() - llg_warp_ring_bytes());   // llg_warp_ring(ring) = this warp's region
+    const int n_general = g.n_items - g.n_int_items, n_a = g.a.n_a_items;
+    const long long n_mixed = (long long)g.n_int_items + n_a;
+    const long long total = n_general + n_mixed;
+    for (;;) {
+        unsigned q = 0;
+        if (lane == 0) q = atomicAdd(queue, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if ((long long)q >= total) break;
+        if ((int)q < n_general) {
+            const LlgLane m = llg_lane_general(p, g, (int)q, lane);
+            llg_vjp_general3_item<HAS_D, HAS_O>(p, g, m, ring, c_u, c_p, g_x0, g_dxdt);
+        } else {
+            const long long r = (long long)q - n_general, a0 = r * n_a / n_mixed, a1 = (r + 1) * n_a / n_mixed;
+            if (a1 > a0) {
+                do_a((int)a0);
+            } else {
+                const LlgLane m = llg_lane_interior(p, g, (int)(r - a0), lane);
+                llg_vjp_lean3_item<HAS_D, HAS_O>(p, g, m, maps, ring0, wid, phases, c_u, c_p, g_x0);
+            }
+        }
+    }
+}
+
 // two CTAs per SM: the loop needs ~246 registers; at 168 (three CTAs) it spills and runs 0.96 ms instead of 0.86 ms (8 x 6 x 2048^2)
 template <bool HAS_D, bool HAS_O>
 __global__ void __launch_bounds__(kLlgThreads, 2)

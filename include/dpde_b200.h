@@ -96,8 +96,8 @@ int dpde_set_fast_path(int enable);
    VJP pass instead of streaming it as separate work items, key 5 = 1 sends the interior work items of the LLG marching kernels
    through their general loop (A/B measurements of the lean loop), key 6 selects the LLG m x H_eff kernels: 0 (default) =
    row-marching kernels on large grids (W >= 128, >= 4 Mi pixels), convert-once tiles otherwise; 1 = tiles always; 2 = marching
-   whenever W >= 128; key 7 = 1 feeds the lean items of the LLG marching reduce pass by cp.async instead of TMA (cp.async.bulk.tensor;
-   the default wherever the tensor maps can be encoded).  TEST / TUNING HOOK like dpde_set_fast_path: process-wide atomics; the per-stream thread-safety of the
+   whenever W >= 128; key 7 = 1 runs the LLG marching kernels without TMA (cp.async.bulk.tensor): reduce pass with the cp.async feed, VJP as the two-CTA
+   kernel with register windows instead of the three-CTA kernel (the TMA forms are the default wherever the tensor maps can be encoded).  TEST / TUNING HOOK like dpde_set_fast_path: process-wide atomics; the per-stream thread-safety of the
    compute entry points does not extend to changing these concurrently. */
 int dpde_set_tuning(int key, int value);
 

@@ -104,8 +104,8 @@ def test_llg_residual_full_size_against_the_torch_oracle_on_device(K0):
     eng = GuidanceEngine(B, 6, ch_a, H, W, PDE_LLG_RESIDUAL, dev, obs_a=obs_a, mask_a=mask_a, obs_u=obs_u, mask_u=mask_u,
                          sample_coef=field / (1000 * c.mu0), dx=dx, llg=c)
     gx, gd = eng.seed(x0, dxdt, w, want_dxdt_grad=True)
-    gx2, _ = eng.seed(x0, dxdt, w)                       # without d / d dmdt the VJP takes its lean interior loop
-    assert torch.equal(gx, gx2)
+    gx2, _ = eng.seed(x0, dxdt, w)                       # without d / d dmdt the VJP runs its three-CTA kernel (TMA-fed lean items,
+    assert _rel(gx2, gx) < 1e-6                          # scatter form: the fp64 rounding differs, an fp32 result may move by one ulp)
     from dynamical_pde_diffusion_b200 import _ffi
     s_tma = eng.scalars[:4].clone()
     try:                                                 # reduce pass fed by cp.async instead of TMA: same bits

@@ -346,9 +346,9 @@ def test_llg_residual_marching_kernels(shape, rows, want_d):
     try:
         _ffi.check(T(2, rows))
         _ffi.check(T(6, 2))
-        s_m, g_m, gd_m = run()                    # marching, lean loop where the geometry allows it (reduce pass: TMA-fed ring)
+        s_m, g_m, gd_m = run()                    # marching, lean loop where the geometry allows it (TMA-fed; VJP: three-CTA kernel)
         _ffi.check(T(7, 1))
-        s_c, g_c, gd_c = run()                    # the same with the cp.async feed in the reduce pass
+        s_c, g_c, gd_c = run()                    # the same without TMA: cp.async feed in the reduce pass, two-CTA VJP kernel
         _ffi.check(T(7, 0))
         _ffi.check(T(5, 1))
         s_g, g_g, gd_g = run()                    # marching, general loop only
@@ -359,7 +359,8 @@ def test_llg_residual_marching_kernels(shape, rows, want_d):
     finally:
         for k in (2, 5, 6, 7):
             _ffi.check(T(k, 0))
-    assert torch.equal(s_c, s_m) and torch.equal(g_c, g_m), "TMA-fed and cp.async-fed reduce passes differ"
+    assert torch.equal(s_c, s_m), "TMA-fed and cp.async-fed reduce passes differ"
+    _close(g_c, g_m, 2e-7, "seed, three-CTA VJP kernel vs two-CTA kernel")    # scatter form: fp64 rounding differs, fp32 results may move by one ulp
     loss, gm_ref, gd_ref = R.llg_residual_guidance_numpy(x0[:, ch_a:].double().numpy(), dxdt[:, ch_a:].double().numpy(),
                                                          field.numpy(), dx, rc, w_pde=w[2])
     mu = np.broadcast_to(mask_u.double().numpy(), (B, 3, H, W))
