@@ -717,7 +717,10 @@ __device__ __forceinline__ LlgLane llg_lane_interior(const Params& p, const LlgM
     return m;
 }
 
-template <bool HAS_D, bool HAS_O>
+// EDGE: the item is an edge strip (first / last) of an interior chunk: rows need no reflection, so it takes this TMA-fed form too (a box
+// may start at column -4 or end beyond W: TMA fills what lies outside with zeros); the lane on the edge column reflects its missing
+// neighbour and the transposed stencil gets its column weights.
+template <bool HAS_D, bool HAS_O, bool EDGE>
 __device__ __forceinline__ void llg_vjp_lean3_item(const Params& p, const LlgMarchGeom& g, const LlgLane& m, const LlgTmaMaps& maps, unsigned ring0,
                                                    int wid, unsigned& phases, double c_u, double c_p, float* __restrict__ g_x0) {
     const unsigned lane = threadIdx.x & 31;
@@ -781,6 +784,9 @@ __device__ __forceinline__ void llg_vjp_lean3_item(const Params& p, const LlgMar
     Mask3 mk = masks(m.ys - 1);                                       // masks of the row evaluated in THIS iteration
     wait(0);
     unsigned sa = 0, sb = 1;                                          // slots of pairs q, q + 1
+    // column weights of the transposed stencil (EDGE): a neighbour counts twice when it lies on an edge column, not at all outside
+    const double wl0 = !EDGE ? 1.0 : (m.left_edge ? 0.0 : (m.col0 - 1 == 0 ? 2.0 : 1.0)), wl1 = !EDGE ? 1.0 : (m.col0 == 0 ? 2.0 : 1.0);
+    const double wr0 = !EDGE ? 1.0 : (m.col0 + 1 == p.W - 1 ? 2.0 : 1.0), wr1 = !EDGE ? 1.0 : (m.right_edge ? 0.0 : (m.col0 + 2 == p.W - 1 ? 2.0 : 1.0));
 
     // one iteration: rows y - 1, y, y + 1 at (slot, box row) su/ru, sc/rc, sd/rd; y = r0 + it + 1
     auto row = [&](int it, unsigned su, int ru, unsigned sc_, int rc, unsigned sd, int rd) {
@@ -792,7 +798,11 @@ __device__ __forceinline__ void llg_vjp_lean3_item(const Params& p, const LlgMar
         for (int c = 0; c < 3; ++c) {
             const unsigned ac = at(sc_, 0, c, rc);
             const float2 fc = lds64f(ac), fu = lds64f(at(su, 0, c, ru)), fd = lds64f(at(sd, 0, c, rd));
-            const float fl = __uint_as_float(lds32(ac - 4)), fr = __uint_as_float(lds32(ac + 8));
+            float fl = __uint_as_float(lds32(ac - 4)), fr = __uint_as_float(lds32(ac + 8));
+            if (EDGE) {
+                if (m.left_edge) fl = fc.y;                           // reflect: m[-1] = m[1]
+                if (m.right_edge) fr = fc.x;
+            }
             mc.v[c][0] = (double)fc.x;
             mc.v[c][1] = (double)fc.y;
             const double up[2] = {(double)fu.x, (double)fu.y}, dn[2] = {(double)fd.x, (double)fd.y};
@@ -821,8 +831,14 @@ __device__ __forceinline__ void llg_vjp_lean3_item(const Params& p, const LlgMar
             const double o0 = fma(ck, g0.v[c][0], P.v[c][0]), o1 = fma(ck, g0.v[c][1], P.v[c][1]);
             if (emit) *reinterpret_cast<float2*>(gm + c * plane + (int64_t)(y - 1) * W) = make_float2((float)o0, (float)o1);
             const double l = __shfl_up_sync(0xffffffffu, g0.v[c][1], 1), q = __shfl_down_sync(0xffffffffu, g0.v[c][0], 1);
-            const double a0 = (gp.v[c][0] + (l + g0.v[c][1])) - 4.0 * g0.v[c][0];
-            const double a1 = (gp.v[c][1] + (g0.v[c][0] + q)) - 4.0 * g0.v[c][1];
+            double a0, a1;
+            if (EDGE) {
+                a0 = (gp.v[c][0] + (wl0 * l + wr0 * g0.v[c][1])) - 4.0 * g0.v[c][0];
+                a1 = (gp.v[c][1] + (wl1 * g0.v[c][0] + wr1 * q)) - 4.0 * g0.v[c][1];
+            } else {
+                a0 = (gp.v[c][0] + (l + g0.v[c][1])) - 4.0 * g0.v[c][0];
+                a1 = (gp.v[c][1] + (g0.v[c][0] + q)) - 4.0 * g0.v[c][1];
+            }
             double v0 = fma(ck, a0, cl * ln.v[c][0]), v1 = fma(ck, a1, cl * ln.v[c][1]);
             if (HAS_O) {
                 fma_where(v0, c_u, mc.v[c][0] - ob6.v[c][0], mask_bit(mk, c, 0));
@@ -1013,6 +1029,7 @@ llg_vjp_lean3_kernel(const __grid_constant__ Params p, const __grid_constant__ L
     };
     unsigned char* ring = ring_mem + (tid >> 5) * (llg_v3_warp_bytes() - llg_warp_ring_bytes());   // llg_warp_ring(ring) = this warp's region
     const int n_general = g.n_items - g.n_int_items, n_a = g.a.n_a_items;
+    const int n_boundary = (g.chunks - (g.c_hi - g.c_lo + 1)) * g.strips * p.B;   // first part of the general order (llg_lane_general)
     const long long n_mixed = (long long)g.n_int_items + n_a;
     const long long total = n_general + n_mixed;
     for (;;) {
@@ -1022,14 +1039,17 @@ llg_vjp_lean3_kernel(const __grid_constant__ Params p, const __grid_constant__ L
         if ((long long)q >= total) break;
         if ((int)q < n_general) {
             const LlgLane m = llg_lane_general(p, g, (int)q, lane);
-            llg_vjp_general3_item<HAS_D, HAS_O>(p, g, m, ring, c_u, c_p, g_x0, g_dxdt);
+            if ((int)q < n_boundary)                                  // boundary chunks: reflected rows, cp.async ring
+                llg_vjp_general3_item<HAS_D, HAS_O>(p, g, m, ring, c_u, c_p, g_x0, g_dxdt);
+            else                                                      // edge strips of interior chunks
+                llg_vjp_lean3_item<HAS_D, HAS_O, true>(p, g, m, maps, ring0, wid, phases, c_u, c_p, g_x0);
         } else {
             const long long r = (long long)q - n_general, a0 = r * n_a / n_mixed, a1 = (r + 1) * n_a / n_mixed;
             if (a1 > a0) {
                 do_a((int)a0);
             } else {
                 const LlgLane m = llg_lane_interior(p, g, (int)(r - a0), lane);
-                llg_vjp_lean3_item<HAS_D, HAS_O>(p, g, m, maps, ring0, wid, phases, c_u, c_p, g_x0);
+                llg_vjp_lean3_item<HAS_D, HAS_O, false>(p, g, m, maps, ring0, wid, phases, c_u, c_p, g_x0);
             }
         }
     }
