@@ -127,6 +127,52 @@ struct Mask3 {
     unsigned k[3];
 };
 
+// interior item index -> lane geometry (batch innermost, then strip, then chunk, inside the interior rectangle)
+__device__ __forceinline__ LlgLane llg_lane_interior(const Params& p, const LlgMarchGeom& g, int idx, int lane) {
+    LlgLane m;
+    const unsigned ns = (unsigned)(g.s_hi - g.s_lo + 1), t = (unsigned)idx / (unsigned)p.B;
+    m.b = (int)((unsigned)idx - t * p.B);
+    const unsigned cq = t / ns;
+    const int strip = g.s_lo + (int)(t - cq * ns), chunk = g.c_lo + (int)cq;
+    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
+    m.lane_ok = true;
+    m.out_ok = lane >= 1 && lane <= 30;
+    m.colc = m.col0;
+    m.left_edge = m.right_edge = false;
+    m.ys = p.ylo + chunk * g.R;
+    m.ye = m.ys + g.R;
+    return m;
+}
+
+// general (edge) item index -> (strip, chunk, b): first the boundary chunks of every strip, then the edge strips of the interior chunks
+__device__ __forceinline__ LlgLane llg_lane_general(const Params& p, const LlgMarchGeom& g, int idx, int lane) {
+    const int nc = g.c_hi - g.c_lo + 1, ns = g.s_hi - g.s_lo + 1;
+    const int n_boundary = (g.chunks - nc) * g.strips * p.B;
+    int strip, chunk;
+    const unsigned t = (unsigned)(idx < n_boundary ? idx : idx - n_boundary) / (unsigned)p.B;
+    const int b = (int)((unsigned)(idx < n_boundary ? idx : idx - n_boundary) - t * p.B);
+    if (idx < n_boundary) {
+        const int cq = (int)(t / (unsigned)g.strips);
+        strip = (int)(t - (unsigned)cq * g.strips);
+        chunk = cq < g.c_lo ? cq : g.c_hi + 1 + (cq - g.c_lo);
+    } else {
+        const int es = g.strips - ns, cq = (int)(t / (unsigned)es), e = (int)(t - (unsigned)cq * es);
+        chunk = g.c_lo + cq;
+        strip = e < g.s_lo ? e : g.s_hi + 1 + (e - g.s_lo);
+    }
+    LlgLane m;
+    m.b = b;
+    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
+    m.lane_ok = m.col0 >= 0 && m.col0 < p.W;
+    m.out_ok = m.lane_ok && lane >= 1 && lane <= 30;
+    m.colc = m.lane_ok ? m.col0 : 0;
+    m.left_edge = m.col0 == 0;
+    m.right_edge = m.col0 + 2 == p.W;
+    m.ys = p.ylo + chunk * g.R;
+    m.ye = min(m.ys + g.R, p.yhi);
+    return m;
+}
+
 struct V6 {
     double v[3][2];                          // [component][pixel of the lane]
 };
@@ -431,7 +477,7 @@ struct LlgTmaFeed {
 // `wid` (warp index in the CTA) and the coordinates are values the compiler KNOWS to be warp-uniform (shuffle broadcasts) and the
 // issuing lane comes from elect.sync: then UTMALDG takes its operands from uniform registers directly; with per-lane values or
 // `lane == 0` ptxas wraps every copy in an ELECT / R2UR.BROADCAST loop (~10 instructions per copy).
-template <bool HAS_D, bool HAS_O>
+template <bool HAS_D, bool HAS_O, bool EDGE>
 __device__ __forceinline__ void llg_march_reduce_item_tma(const Params& p, const LlgMarchGeom& g, const LlgLane& m, const LlgTmaMaps& maps,
                                                           unsigned char* ring_mem, unsigned ring0, int wid, unsigned& phases, double& s_u,
                                                           double& s_p) {
@@ -469,7 +515,11 @@ __device__ __forceinline__ void llg_march_reduce_item_tma(const Params& p, const
         double lap[3][2];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const double lf = __shfl_up_sync(0xffffffffu, mc.v[c][1], 1), rt = __shfl_down_sync(0xffffffffu, mc.v[c][0], 1);
+            double lf = __shfl_up_sync(0xffffffffu, mc.v[c][1], 1), rt = __shfl_down_sync(0xffffffffu, mc.v[c][0], 1);
+            if (EDGE) {                                               // edge strip of an interior chunk: the lane on the edge column reflects
+                if (m.left_edge) lf = mc.v[c][1];
+                if (m.right_edge) rt = mc.v[c][0];
+            }
             lap2(mu.v[c], mc.v[c], md.v[c], lf, rt, lap[c]);
         }
 #pragma unroll
@@ -542,14 +592,55 @@ llg_march_reduce_kernel(const __grid_constant__ Params p, const __grid_constant_
         if (TMA) interior = __shfl_sync(0xffffffffu, (int)interior, 0) != 0;   // uniform by construction; now the compiler knows it too
         if (interior) {                                                // warp-uniform: one strip per warp
             if (TMA)
-                llg_march_reduce_item_tma<HAS_D, HAS_O>(p, g, m, maps, ring, ring0, wid, phases, s_u, s_p);
+                llg_march_reduce_item_tma<HAS_D, HAS_O, false>(p, g, m, maps, ring, ring0, wid, phases, s_u, s_p);
             else
                 llg_march_reduce_item<HAS_D, HAS_O, true>(p, g, m, ring, s_u, s_p);
         } else {
             llg_march_reduce_item<HAS_D, HAS_O, false>(p, g, m, ring, s_u, s_p);
         }
     };
-    run_interleaved(warp0, nwarps, g.n_items, p.has_a ? g.a.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+    const int n_boundary = g.n_int_items > 0 ? (g.chunks - (g.c_hi - g.c_lo + 1)) * g.strips * p.B : 0;
+    if (TMA && g.n_int_items > 0 && n_boundary <= nwarps) {
+        // Static longest-first order (the sums must not depend on timing, so no dynamic queue here): round 0 gives the slow boundary-chunk
+        // items to warps 0 .. n_boundary - 1 and keeps round 1 free for them (such an item costs about two lean ones); every other
+        // (round, warp) position takes the next of: edge strips of interior chunks (TMA-fed, reflecting lanes), then the interior items.
+        // Before, the last chunk's boundary items were the last items of the round-robin and the pass ended on them.
+        const int n_general = g.n_items - g.n_int_items, n_rest = g.n_items - n_boundary;
+        const int rounds = (n_rest + 2 * n_boundary + nwarps - 1) / nwarps;
+        const int n_a = p.has_a ? g.a.n_a_items : 0, na_w = n_a > warp0 ? (n_a - warp0 + nwarps - 1) / nwarps : 0;
+        auto do_round = [&](int r) {
+            if (warp0 < n_boundary && r < 2) {
+                if (r == 0) {
+                    const LlgLane m = llg_lane_general(p, g, warp0, lane);
+                    llg_march_reduce_item<HAS_D, HAS_O, false>(p, g, m, ring, s_u, s_p);
+                }
+                return;
+            }
+            const int pos = r * nwarps + warp0 - (r < 2 ? r * n_boundary + min(warp0, n_boundary) : 2 * n_boundary);
+            if (pos >= n_rest) return;
+            if (pos < n_general - n_boundary) {
+                const LlgLane m = llg_lane_general(p, g, n_boundary + pos, lane);
+                llg_march_reduce_item_tma<HAS_D, HAS_O, true>(p, g, m, maps, ring, ring0, wid, phases, s_u, s_p);
+            } else {
+                const LlgLane m = llg_lane_interior(p, g, pos - (n_general - n_boundary), lane);
+                llg_march_reduce_item_tma<HAS_D, HAS_O, false>(p, g, m, maps, ring, ring0, wid, phases, s_u, s_p);
+            }
+        };
+        int ju = 0, ja = 0;
+        const int a_first = (tid >> 5) & 1;
+        while (ju < rounds || ja < na_w) {                            // u rounds and a-plane items of this warp, mixed in proportion
+            const long long lhs = (long long)ju * na_w, rhs = (long long)ja * rounds;
+            if (ju < rounds && (ja >= na_w || (a_first ? lhs < rhs : lhs <= rhs))) {
+                do_round(ju);
+                ++ju;
+            } else {
+                do_a(warp0 + ja * nwarps);
+                ++ja;
+            }
+        }
+    } else {
+        run_interleaved(warp0, nwarps, g.n_items, p.has_a ? g.a.n_a_items : 0, (tid >> 5) & 1, do_u, do_a);
+    }
     reduce_epilogue_n<kLlgThreads>(p, s_a, s_u, s_p, scratch, &is_last, partials, ticket, sums, finalize, scal, trace);
 }
 
@@ -699,23 +790,6 @@ __device__ __forceinline__ void llg_march_vjp_item(const Params& p, const LlgMar
 constexpr int kLlgV3Slots = 3;
 __host__ __device__ constexpr int llg_v3_warp_bytes() { return kLlgV3Slots * 3 * kLlgBoxPitch; }                     // 14976
 __host__ __device__ constexpr int llg_v3_smem_bytes() { return (kLlgThreads / 32) * (llg_v3_warp_bytes() + kLlgV3Slots * 8); }
-
-// interior item index -> lane geometry (batch innermost, then strip, then chunk, inside the interior rectangle)
-__device__ __forceinline__ LlgLane llg_lane_interior(const Params& p, const LlgMarchGeom& g, int idx, int lane) {
-    LlgLane m;
-    const unsigned ns = (unsigned)(g.s_hi - g.s_lo + 1), t = (unsigned)idx / (unsigned)p.B;
-    m.b = (int)((unsigned)idx - t * p.B);
-    const unsigned cq = t / ns;
-    const int strip = g.s_lo + (int)(t - cq * ns), chunk = g.c_lo + (int)cq;
-    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
-    m.lane_ok = true;
-    m.out_ok = lane >= 1 && lane <= 30;
-    m.colc = m.col0;
-    m.left_edge = m.right_edge = false;
-    m.ys = p.ylo + chunk * g.R;
-    m.ye = m.ys + g.R;
-    return m;
-}
 
 // EDGE: the item is an edge strip (first / last) of an interior chunk: rows need no reflection, so it takes this TMA-fed form too (a box
 // may start at column -4 or end beyond W: TMA fills what lies outside with zeros); the lane on the edge column reflects its missing
@@ -966,35 +1040,6 @@ __device__ __forceinline__ void llg_vjp_general3_item(const Params& p, const Llg
             row(it, J, sn < n_it + 2, sn < n_it + 1, sn < n_it);
         });
     cp_async_wait<0>();
-}
-
-// general (edge) item index -> (strip, chunk, b): first the boundary chunks of every strip, then the edge strips of the interior chunks
-__device__ __forceinline__ LlgLane llg_lane_general(const Params& p, const LlgMarchGeom& g, int idx, int lane) {
-    const int nc = g.c_hi - g.c_lo + 1, ns = g.s_hi - g.s_lo + 1;
-    const int n_boundary = (g.chunks - nc) * g.strips * p.B;
-    int strip, chunk;
-    const unsigned t = (unsigned)(idx < n_boundary ? idx : idx - n_boundary) / (unsigned)p.B;
-    const int b = (int)((unsigned)(idx < n_boundary ? idx : idx - n_boundary) - t * p.B);
-    if (idx < n_boundary) {
-        const int cq = (int)(t / (unsigned)g.strips);
-        strip = (int)(t - (unsigned)cq * g.strips);
-        chunk = cq < g.c_lo ? cq : g.c_hi + 1 + (cq - g.c_lo);
-    } else {
-        const int es = g.strips - ns, cq = (int)(t / (unsigned)es), e = (int)(t - (unsigned)cq * es);
-        chunk = g.c_lo + cq;
-        strip = e < g.s_lo ? e : g.s_hi + 1 + (e - g.s_lo);
-    }
-    LlgLane m;
-    m.b = b;
-    m.col0 = strip * kLlgStrip - 2 + 2 * lane;
-    m.lane_ok = m.col0 >= 0 && m.col0 < p.W;
-    m.out_ok = m.lane_ok && lane >= 1 && lane <= 30;
-    m.colc = m.lane_ok ? m.col0 : 0;
-    m.left_edge = m.col0 == 0;
-    m.right_edge = m.col0 + 2 == p.W;
-    m.ys = p.ylo + chunk * g.R;
-    m.ye = min(m.ys + g.R, p.yhi);
-    return m;
 }
 
 // Work queue (one atomic counter per launch): the slow general items first, then the lean items with the a-plane items mixed in evenly --

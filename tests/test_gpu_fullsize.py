@@ -108,10 +108,10 @@ def test_llg_residual_full_size_against_the_torch_oracle_on_device(K0):
     assert _rel(gx2, gx) < 1e-6                          # scatter form: the fp64 rounding differs, an fp32 result may move by one ulp)
     from dynamical_pde_diffusion_b200 import _ffi
     s_tma = eng.scalars[:4].clone()
-    try:                                                 # reduce pass fed by cp.async instead of TMA: same bits
+    try:                                                 # reduce pass fed by cp.async (round-robin item order) instead of TMA
         _ffi.check(_ffi.lib().dpde_set_tuning(7, 1))
         eng.reduce(x0, dxdt, w)
-        assert torch.equal(eng.scalars[:4], s_tma)
+        assert torch.allclose(eng.scalars[:4], s_tma, rtol=1e-12, atol=0)     # other item order: the last bits of the fp64 sums may differ
     finally:
         _ffi.check(_ffi.lib().dpde_set_tuning(7, 0))
     losses, gx_ref, gd_ref = _torch_guidance(x0, dxdt, obs_a, obs_u, mask_a, mask_u, ch_a,

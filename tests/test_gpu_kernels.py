@@ -359,7 +359,7 @@ def test_llg_residual_marching_kernels(shape, rows, want_d):
     finally:
         for k in (2, 5, 6, 7):
             _ffi.check(T(k, 0))
-    assert torch.equal(s_c, s_m), "TMA-fed and cp.async-fed reduce passes differ"
+    _close(s_c, s_m, 1e-13, "sums, TMA-fed reduce pass (longest-first item order) vs cp.async feed (round-robin order)")
     _close(g_c, g_m, 2e-7, "seed, three-CTA VJP kernel vs two-CTA kernel")    # scatter form: fp64 rounding differs, fp32 results may move by one ulp
     loss, gm_ref, gd_ref = R.llg_residual_guidance_numpy(x0[:, ch_a:].double().numpy(), dxdt[:, ch_a:].double().numpy(),
                                                          field.numpy(), dx, rc, w_pde=w[2])
