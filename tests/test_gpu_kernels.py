@@ -479,6 +479,70 @@ def test_row_slab_decomposition_equals_whole_grid(kind_name, n_slabs, kernel_pat
         assert torch.all(g[..., :halo, :] == 0) and torch.all(g[..., -halo:, :] == 0)   # ghost rows never written
 
 
+@pytest.mark.parametrize("rows", [8, 14])
+@pytest.mark.parametrize("n_slabs", [2, 3])
+def test_llg_marching_kernels_on_row_slabs(rows, n_slabs):
+    """The row-marching LLG kernels on row slabs (ghost rows, global reflection only at the global top / bottom): chunk length 8 gives
+    the reduce pass TMA-fed lean items, 14 gives the VJP its three-CTA kernel (TMA-fed lean items, light general items, work queue);
+    no d / d dmdt output, which would send the VJP to its two-CTA kernel.  Against the whole grid and against the kernels without TMA."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_LLG_RESIDUAL
+
+    dev, halo, B, ch_a, H, W, dx = _dev(), 2, 2, 3, 120, 260, 500e-9 / 64
+    gen = torch.Generator().manual_seed(17 + rows)
+    x0 = torch.randn(B, 6, H, W, generator=gen).to(dev)
+    dxdt = (0.01 * torch.randn(B, 6, H, W, generator=gen)).to(dev)
+    obs_a, obs_u = torch.randn(1, 3, H, W, generator=gen).to(dev), torch.randn(1, 3, H, W, generator=gen).to(dev)
+    mask_a, mask_u = (torch.rand(H, W, generator=gen) < 0.3).to(dev), (torch.rand(H, W, generator=gen) < 0.2).to(dev)
+    coef, w = (1e4 * torch.randn(B, 3, generator=gen)).double().to(dev), (5.0, 0.5, 7.0)
+    bounds = [H * r // n_slabs for r in range(n_slabs + 1)]
+
+    def pad(t, r0, r1):
+        out = torch.zeros(*t.shape[:-2], r1 - r0 + 2 * halo, W, dtype=t.dtype, device=dev)
+        lo, hi = max(r0 - halo, 0), min(r1 + halo, H)
+        out[..., lo - (r0 - halo): hi - (r0 - halo), :] = t[..., lo:hi, :]
+        return out
+
+    def run():
+        whole = GuidanceEngine(B, 6, ch_a, H, W, PDE_LLG_RESIDUAL, dev, obs_a=obs_a, mask_a=mask_a, obs_u=obs_u, mask_u=mask_u, sample_coef=coef,
+                               dx=dx, llg=LLGConstants())
+        g_ref, _ = whole.seed(x0, dxdt, w)
+        engines, total = [], torch.zeros(3, dtype=torch.float64, device=dev)
+        for r in range(n_slabs):
+            r0, r1 = bounds[r], bounds[r + 1]
+            e = GuidanceEngine(B, 6, ch_a, r1 - r0 + 2 * halo, W, PDE_LLG_RESIDUAL, dev, obs_a=pad(obs_a, r0, r1), mask_a=pad(mask_a, r0, r1),
+                               obs_u=pad(obs_u, r0, r1), mask_u=pad(mask_u, r0, r1), sample_coef=coef, dx=dx, llg=LLGConstants(),
+                               slab=dict(halo=halo, row0=r0, H_global=H, has_a=True, has_u=True))
+            xl, dl = pad(x0, r0, r1), pad(dxdt, r0, r1)
+            e.reduce(xl, dl, w, finalize=False)
+            total += e.sums
+            engines.append((e, xl, dl, r0, r1))
+        _close(total, whole.sums, 1e-12, "slab sums")
+        pieces = []
+        for e, xl, dl, r0, r1 in engines:
+            e.sums.copy_(total)
+            e.finalize()
+            g, _ = e.vjp(xl, dl, w)
+            _close(g[..., halo:-halo, :], g_ref[..., r0:r1, :], 2e-6, "slab gradient")
+            assert torch.all(g[..., :halo, :] == 0) and torch.all(g[..., -halo:, :] == 0)      # ghost rows never written
+            pieces.append(g[..., halo:-halo, :])
+        return whole.sums.clone(), g_ref, torch.cat(pieces, dim=-2)
+
+    T = _ffi.lib().dpde_set_tuning
+    try:
+        _ffi.check(T(6, 2))
+        _ffi.check(T(2, rows))
+        s1, gw1, gs1 = run()                       # TMA forms
+        _ffi.check(T(7, 1))
+        s0, gw0, gs0 = run()                       # cp.async feed, two-CTA VJP kernel
+    finally:
+        for k in (2, 6, 7):
+            _ffi.check(T(k, 0))
+    _close(s1, s0, 1e-13, "sums with / without TMA")
+    _close(gw1, gw0, 2e-7, "whole-grid seed with / without TMA")
+    _close(gs1, gs0, 2e-7, "slab seeds with / without TMA")
+
+
 def test_halo_pack_unpack_roundtrip():
     import ctypes as C
     from dynamical_pde_diffusion_b200 import _ffi
