@@ -543,6 +543,44 @@ def test_llg_marching_kernels_on_row_slabs(rows, n_slabs):
     _close(gs1, gs0, 2e-7, "slab seeds with / without TMA")
 
 
+def test_llg_vjp_work_queue_counters_wrap_around():
+    """The three-CTA LLG VJP kernel takes one zeroed work-queue counter per launch from a ring of 256 device slots: 600 launches wrap
+    the ring twice, on two streams; every launch must reproduce the first result bit for bit."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_LLG_RESIDUAL
+
+    dev, B, H, W = _dev(), 2, 64, 260
+    gen = torch.Generator().manual_seed(23)
+    x0, dxdt = torch.randn(B, 6, H, W, generator=gen).to(dev), (0.01 * torch.randn(B, 6, H, W, generator=gen)).to(dev)
+    obs_a, obs_u = torch.randn(1, 3, H, W, generator=gen).to(dev), torch.randn(1, 3, H, W, generator=gen).to(dev)
+    mask = (torch.rand(H, W, generator=gen) < 0.2).to(dev)
+    coef = (1e4 * torch.randn(B, 3, generator=gen)).double().to(dev)
+    T = _ffi.lib().dpde_set_tuning
+    try:
+        _ffi.check(T(6, 2))
+        _ffi.check(T(2, 14))
+        eng = GuidanceEngine(B, 6, 3, H, W, PDE_LLG_RESIDUAL, dev, obs_a=obs_a, mask_a=mask, obs_u=obs_u, mask_u=mask, sample_coef=coef,
+                             dx=500e-9 / 64, llg=LLGConstants())
+        first, _ = eng.seed(x0, dxdt, (10.0, 0.5, 10.0))
+        first = first.clone()
+        side = torch.cuda.Stream()
+        for i in range(600):
+            if i % 2:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    g, _ = eng.vjp(x0, dxdt, (10.0, 0.5, 10.0))
+                torch.cuda.current_stream().wait_stream(side)
+            else:
+                g, _ = eng.vjp(x0, dxdt, (10.0, 0.5, 10.0))
+            if i % 50 == 49:
+                assert torch.equal(g, first), f"launch {i} differs"
+        torch.cuda.synchronize()
+        assert torch.equal(g, first)
+    finally:
+        for k in (2, 6):
+            _ffi.check(T(k, 0))
+
+
 def test_halo_pack_unpack_roundtrip():
     import ctypes as C
     from dynamical_pde_diffusion_b200 import _ffi
