@@ -543,6 +543,45 @@ def test_llg_marching_kernels_on_row_slabs(rows, n_slabs):
     _close(gs1, gs0, 2e-7, "slab seeds with / without TMA")
 
 
+@pytest.mark.parametrize("variant", ["no_dxdt", "no_obs_u", "no_a_planes", "batch1_ragged"])
+def test_llg_marching_tma_forms_match_the_fallbacks_on_every_template_variant(variant):
+    """TMA-fed reduce pass / three-CTA VJP kernel against the cp.async reduce pass / two-CTA VJP kernel (tuning key 7) for the template
+    variants the other tests do not reach: no time derivative, empty observation mask, no a-planes, batch 1 on a ragged width."""
+    from dynamical_pde_diffusion_b200 import GuidanceEngine, LLGConstants, _ffi
+    from dynamical_pde_diffusion_b200._ffi import PDE_LLG_RESIDUAL
+
+    dev = _dev()
+    B, ch_a, H, W = {"no_dxdt": (2, 3, 64, 260), "no_obs_u": (2, 3, 64, 260), "no_a_planes": (3, 0, 48, 388), "batch1_ragged": (1, 3, 80, 452)}[variant]
+    gen = torch.Generator().manual_seed(len(variant))
+    x0 = torch.randn(B, ch_a + 3, H, W, generator=gen).to(dev)
+    dxdt = None if variant == "no_dxdt" else (0.01 * torch.randn(B, ch_a + 3, H, W, generator=gen)).to(dev)
+    obs_u = torch.randn(1, 3, H, W, generator=gen).to(dev)
+    mask_u = (torch.rand(H, W, generator=gen) < (0.0 if variant == "no_obs_u" else 0.2)).to(dev)
+    obs_a = torch.randn(1, 3, H, W, generator=gen).to(dev) if ch_a else None
+    mask_a = (torch.rand(H, W, generator=gen) < 0.3).to(dev) if ch_a else None
+    coef = (1e4 * torch.randn(B, 3, generator=gen)).double().to(dev)
+    T = _ffi.lib().dpde_set_tuning
+
+    def run():
+        eng = GuidanceEngine(B, ch_a + 3, ch_a, H, W, PDE_LLG_RESIDUAL, dev, obs_a=obs_a, mask_a=mask_a, obs_u=obs_u, mask_u=mask_u,
+                             sample_coef=coef, dx=500e-9 / 64, llg=LLGConstants())
+        g, _ = eng.seed(x0, dxdt, (10.0, 0.5, 10.0))
+        return eng.scalars[:4].clone(), g
+
+    for rows in (8, 14):                                  # 8: lean items in the reduce pass, 14: in the VJP
+        try:
+            _ffi.check(T(6, 2))
+            _ffi.check(T(2, rows))
+            s1, g1 = run()
+            _ffi.check(T(7, 1))
+            s0, g0 = run()
+        finally:
+            for k in (2, 6, 7):
+                _ffi.check(T(k, 0))
+        _close(s1, s0, 1e-13, f"sums ({variant}, rows {rows})")
+        _close(g1, g0, 2e-7, f"seed ({variant}, rows {rows})")
+
+
 def test_llg_vjp_work_queue_counters_wrap_around():
     """The three-CTA LLG VJP kernel takes one zeroed work-queue counter per launch from a ring of 256 device slots: 600 launches wrap
     the ring twice, on two streams; every launch must reproduce the first result bit for bit."""
