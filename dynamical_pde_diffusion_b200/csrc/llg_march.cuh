@@ -23,6 +23,11 @@
 //   * the algebra is arranged for the fp64 pipe (the VJP needs ~100 fp64 instructions per pixel, as long as its 60 B of
 //     HBM traffic): r = dmdt + tau gamma a + tau alpha m x a;  with q = r x m and t = gamma r + alpha q:
 //     G_H = -gamma q - alpha q x m,  G_m = -(H x t) - alpha a x r;  the seed coefficient c_p multiplies the sums once.
+//   * (later in round 2) the lean interior items of the reduce pass are fed by TMA (LlgTmaFeed: cp.async.bulk.tensor boxes of 68 columns x
+//     2 rows x 3 planes, one mbarrier per ring slot and warp) and ordered longest first; the VJP of large grids runs in
+//     llg_vjp_lean3_kernel at three CTAs per SM: rows kept in shared memory instead of register windows, scatter form of the transposed
+//     stencil, TMA-fed lean items, a dynamic longest-first work queue.  The cp.async forms below remain as the fallback (no tensor map,
+//     d / d dmdt wanted, tuning key 7) and serve the general (edge) items.
 // Masks are 0 / 1 bytes (DPDE_U8): observation terms are predicated DFMAs.  Arithmetic and accumulation are fp64.
 //
 // Eligibility (host): as llg_tile.cuh (fp32 fields, W % 4 == 0, aligned bases, fp32 observations, uint8 masks) and W >= 128.
