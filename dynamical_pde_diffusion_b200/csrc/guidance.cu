@@ -981,11 +981,12 @@ int launch_llg_tile_vjp(const Params& p, const LlgGeom& L, const double* scal, c
 }
 
 // ---- LLG m x H_eff residual, marching kernels (llg_march.cuh) ---------------------------------------------
-// Large grids only: measured on 8 x 6 x 2048^2 the marching pair runs 0.41 / 0.86 ms against 0.52 / 0.94 ms of the tile kernels,
-// on config 3's shard (32 x 6 x 128^2, L2 resident) 26 / 39 us against 19 / 21 us -- the tiles keep the small problems.
+// Large grids only.  Measured (profiles/r2y_probe_llg_crossover*.log, reduce / VJP per launch): 8 x 6 x 2048^2 marching 0.30 / 0.55 ms against
+// 0.52 / 0.94 ms of the tile kernels; 2 Mi pixels (8 x 512^2, 32 x 256^2) 32 / 56-61 us against 42 / 65-67 us; 1 Mi pixels 25-28 / 40 us
+// against 30 / 40 us (a tie); config 3's shard (32 x 6 x 128^2, L2 resident) 26 / 35 us against ~20 / 23 us -- marching from 2 Mi pixels up.
 inline bool llg_march_wanted(const Params& p) {
     if (p.kind != DPDE_PDE_LLG_RESIDUAL || p.W < 128 || g_tuning[6] == 1) return false;
-    return g_tuning[6] == 2 || (int64_t)p.B * (p.yhi - p.ylo) * p.W >= (4ll << 20);          // key 6 = 2: marching on every size (tests)
+    return g_tuning[6] == 2 || (int64_t)p.B * (p.yhi - p.ylo) * p.W >= (2ll << 20);          // key 6 = 2: marching on every size (tests)
 }
 
 LlgMarchGeom llg_march_geometry(const Params& p, bool vjp, bool lean_ok) {

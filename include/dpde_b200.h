@@ -95,7 +95,7 @@ int dpde_set_fast_path(int enable);
    VJP, 64 in the reduce pass), keys 3 / 4 = 1 pair every a-plane with the u-plane of the same index in the reduce /
    VJP pass instead of streaming it as separate work items, key 5 = 1 sends the interior work items of the LLG marching kernels
    through their general loop (A/B measurements of the lean loop), key 6 selects the LLG m x H_eff kernels: 0 (default) =
-   row-marching kernels on large grids (W >= 128, >= 4 Mi pixels), convert-once tiles otherwise; 1 = tiles always; 2 = marching
+   row-marching kernels on large grids (W >= 128, >= 2 Mi pixels), convert-once tiles otherwise; 1 = tiles always; 2 = marching
    whenever W >= 128; key 7 = 1 runs the LLG marching kernels without TMA (cp.async.bulk.tensor): reduce pass with the cp.async feed, VJP as the two-CTA
    kernel with register windows instead of the three-CTA kernel (the TMA forms are the default wherever the tensor maps can be encoded).  TEST / TUNING HOOK like dpde_set_fast_path: process-wide atomics; the per-stream thread-safety of the
    compute entry points does not extend to changing these concurrently. */
